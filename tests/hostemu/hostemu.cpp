@@ -1,0 +1,137 @@
+// TEST-ONLY host build of the device arithmetic headers (keaki_b200/csrc/*.cuh).
+//
+// The headers compile for the host with the PTX carry-chain primitives replaced by an emulated
+// carry flag, so the exact algorithm text that runs on the GPU (Montgomery multiplier, tower, curve
+// formulas, Miller loop, final exponentiation, BLAKE3) can be checked against oracle/ on a box
+// without a GPU.  This library is built into tests/hostemu/_build/ and is loaded ONLY by tests/;
+// the product library (libkeaki_b200.so) contains no host arithmetic path.
+#include <cstring>
+#include "../../keaki_b200/csrc/pairing.cuh"
+#include "../../keaki_b200/csrc/blake3.cuh"
+#include "../../keaki_b200/csrc/consts_gen.cuh"
+#include "../../keaki_b200/csrc/msm_digits.cuh"
+
+using namespace kb;
+
+static Fq ldq(const uint32_t* p) { return fp_load<FqParams>(p); }
+static Fr ldr(const uint32_t* p) { return fp_load<FrParams>(p); }
+static Fq2 ldq2(const uint32_t* p) { Fq2 r; r.c0 = ldq(p); r.c1 = ldq(p + 8); return r; }
+static void stq(uint32_t* p, const Fq& a) { fp_store<FqParams>(p, a); }
+static void stq2(uint32_t* p, const Fq2& a) { stq(p, a.c0); stq(p + 8, a.c1); }
+static Fq12 ldq12(const uint32_t* p) {
+  Fq12 r;
+  Fq6* h[2] = {&r.c0, &r.c1};
+  for (int j = 0; j < 2; j++) { h[j]->c0 = ldq2(p + (j * 3 + 0) * 16); h[j]->c1 = ldq2(p + (j * 3 + 1) * 16); h[j]->c2 = ldq2(p + (j * 3 + 2) * 16); }
+  return r;
+}
+static void stq12(uint32_t* p, const Fq12& a) {
+  const Fq6* h[2] = {&a.c0, &a.c1};
+  for (int j = 0; j < 2; j++) { stq2(p + (j * 3 + 0) * 16, h[j]->c0); stq2(p + (j * 3 + 1) * 16, h[j]->c1); stq2(p + (j * 3 + 2) * 16, h[j]->c2); }
+}
+static PairingConsts make_consts() {
+  PairingConsts pc;
+  for (int k = 0; k < 3; k++) for (int i = 0; i < 6; i++) pc.frob.g[k][i] = ldq2(consts::FROB_GAMMA + (k * 6 + i) * 16);
+  pc.tw_x = ldq2(consts::TW_X);
+  pc.tw_y = ldq2(consts::TW_Y);
+  return pc;
+}
+static const PairingConsts& pcs() { static PairingConsts pc = make_consts(); return pc; }
+
+extern "C" {
+
+// op: 0 add, 1 sub, 2 mul, 3 neg(a), 4 inv(a), 5 from_mont(a), 6 to_mont(a), 7 sqr(a); field: 0 Fq, 1 Fr
+void he_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, int n) {
+  for (int i = 0; i < n; i++) {
+    if (field == 0) {
+      Fq x = ldq(a + 8 * i), y = ldq(b + 8 * i), r;
+      switch (op) { case 0: r = x + y; break; case 1: r = x - y; break; case 2: r = x * y; break; case 3: r = -x; break;
+        case 4: r = inv(x); break; case 5: r = fp_from_mont<FqParams>(x); break; case 6: r = fp_to_mont<FqParams>(x); break; default: r = sqr(x); }
+      stq(out + 8 * i, r);
+    } else {
+      Fr x = ldr(a + 8 * i), y = ldr(b + 8 * i), r;
+      switch (op) { case 0: r = x + y; break; case 1: r = x - y; break; case 2: r = x * y; break; case 3: r = -x; break;
+        case 4: r = inv(x); break; case 5: r = fp_from_mont<FrParams>(x); break; case 6: r = fp_to_mont<FrParams>(x); break; default: r = sqr(x); }
+      fp_store<FrParams>(out + 8 * i, r);
+    }
+  }
+}
+
+// op: 0 mul, 1 sqr(a), 2 inv(a), 3 mul_xi(a)
+void he_fq2_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  Fq2 x = ldq2(a), y = ldq2(b), r;
+  switch (op) { case 0: r = x * y; break; case 1: r = sqr(x); break; case 2: r = inv(x); break; default: r = mul_xi(x); }
+  stq2(out, r);
+}
+
+// op: 0 mul, 1 sqr(a), 2 inv(a), 3 cyclotomic_sqr(a), 4..6 frobenius k=1..3, 7 conj
+void he_fq12_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  Fq12 x = ldq12(a), y = ldq12(b), r;
+  switch (op) {
+    case 0: r = x * y; break; case 1: r = sqr(x); break; case 2: r = inv(x); break; case 3: r = cyclotomic_sqr(x); break;
+    case 4: case 5: case 6: r = frobenius(x, op - 3, pcs().frob); break; default: r = conj(x);
+  }
+  stq12(out, r);
+}
+
+// easy part of the final exponentiation (maps into the cyclotomic subgroup) - to build inputs for op 3 above
+void he_fq12_easy(const uint32_t* a, uint32_t* out) {
+  Fq12 f = ldq12(a);
+  Fq12 r = conj(f) * inv(f);
+  r = frobenius(r, 2, pcs().frob) * r;
+  stq12(out, r);
+}
+
+// sparse line product: out = a * (l0 + l1 w + l3 w^3)
+void he_mul_by_line(const uint32_t* a, const uint32_t* l0, const uint32_t* l1, const uint32_t* l3, uint32_t* out) {
+  stq12(out, mul_by_line(ldq12(a), ldq2(l0), ldq2(l1), ldq2(l3)));
+}
+
+// G1: out_xy (affine, Montgomery; zeros = infinity) = k * P (k canonical 8 limbs) [+ Q if q != null]
+void he_g1_mul_add(const uint32_t* p_xy, const uint32_t* k, const uint32_t* q_xy, uint32_t* out_xy) {
+  G1Affine p; p.x = ldq(p_xy); p.y = ldq(p_xy + 8);
+  G1 r = ec_mul(to_xyzz(p), k);
+  if (q_xy) { G1Affine q; q.x = ldq(q_xy); q.y = ldq(q_xy + 8); r = ec_add_mixed(r, q); }
+  G1Affine a = to_affine(r);
+  stq(out_xy, a.x); stq(out_xy + 8, a.y);
+}
+// full (non-mixed) addition path: out = k1*P + k2*Q computed separately then ec_add
+void he_g1_lincomb(const uint32_t* p_xy, const uint32_t* k1, const uint32_t* q_xy, const uint32_t* k2, uint32_t* out_xy) {
+  G1Affine p, q; p.x = ldq(p_xy); p.y = ldq(p_xy + 8); q.x = ldq(q_xy); q.y = ldq(q_xy + 8);
+  G1Affine a = to_affine(ec_add(ec_mul(to_xyzz(p), k1), ec_mul(to_xyzz(q), k2)));
+  stq(out_xy, a.x); stq(out_xy + 8, a.y);
+}
+void he_g2_mul_add(const uint32_t* p_xy, const uint32_t* k, const uint32_t* q_xy, uint32_t* out_xy) {
+  G2Affine p; p.x = ldq2(p_xy); p.y = ldq2(p_xy + 16);
+  G2 r = ec_mul(to_xyzz(p), k);
+  if (q_xy) { G2Affine q; q.x = ldq2(q_xy); q.y = ldq2(q_xy + 16); r = ec_add_mixed(r, q); }
+  G2Affine a = to_affine(r);
+  stq2(out_xy, a.x); stq2(out_xy + 16, a.y);
+}
+
+// Miller loop only (Montgomery Fq12 out), full pairing as 384 canonical bytes, and key derivation
+void he_miller(const uint32_t* p_xy, const uint32_t* q_xy, uint32_t* out) {
+  G1Affine p; p.x = ldq(p_xy); p.y = ldq(p_xy + 8);
+  G2Affine q; q.x = ldq2(q_xy); q.y = ldq2(q_xy + 16);
+  stq12(out, miller_loop(p, q, pcs()));
+}
+void he_final_exp(const uint32_t* f, uint32_t* out) { stq12(out, final_exponentiation(ldq12(f), pcs())); }
+void he_pairing_bytes(const uint32_t* p_xy, const uint32_t* q_xy, uint8_t* out384) {
+  G1Affine p; p.x = ldq(p_xy); p.y = ldq(p_xy + 8);
+  G2Affine q; q.x = ldq2(q_xy); q.y = ldq2(q_xy + 16);
+  Fq12 e = final_exponentiation(miller_loop(p, q, pcs()), pcs());
+  uint32_t w[96];
+  gt_to_words(e, w);
+  memcpy(out384, w, 384);
+}
+void he_gt_key(const uint8_t* gt384, const uint8_t* msg, uint8_t* out, uint64_t len) {
+  uint32_t w[96];
+  memcpy(w, gt384, 384);
+  b3_gt_xof_xor(w, msg, out, len);
+}
+
+// signed-digit recoding used by the MSM (window c bits): digits[w] in [-2^(c-1), 2^(c-1)]
+void he_msm_digits(const uint32_t* scalar_canonical, int c, int nwin, int32_t* digits) {
+  msm_signed_digits(scalar_canonical, c, nwin, digits);
+}
+
+}  // extern "C"
