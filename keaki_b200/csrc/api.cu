@@ -1,0 +1,261 @@
+// C ABI of libkeaki_b200.so (declared in include/keaki_b200.h).  Thin: argument checks, staging of
+// host buffers, stream synchronisation and error translation.  There is no host arithmetic and no
+// CPU fallback anywhere behind these entry points.
+#include "ctx.cuh"
+
+using namespace kb;
+
+namespace {
+
+int32_t fail(kb_ctx* ctx, int32_t code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define KB_API_BEGIN(ctx)                          \
+  if (!(ctx)) return KB_ERR_ARG;                   \
+  try {                                            \
+    KB_CUDA(cudaSetDevice((ctx)->device));         \
+    timer_start((ctx), KB_T_TOTAL);
+
+#define KB_API_END(ctx)                                                   \
+    timer_stop((ctx), KB_T_TOTAL);                                        \
+    KB_CUDA(cudaStreamSynchronize((ctx)->stream));                        \
+    timers_collect(ctx);                                                  \
+    return KB_OK;                                                         \
+  } catch (const ApiError& e) { cudaStreamSynchronize((ctx)->stream); return fail((ctx), e.code, e.what());       \
+  } catch (const CudaError& e) { cudaGetLastError(); return fail((ctx), KB_ERR_CUDA, e.what());                  \
+  } catch (const std::exception& e) { return fail((ctx), KB_ERR_CUDA, e.what()); }
+
+void need(bool ok, const char* what) { if (!ok) throw ApiError(KB_ERR_ARG, what); }
+void need_srs(kb_ctx* ctx) { if (!ctx->d_srs) throw ApiError(KB_ERR_NO_SRS, "no SRS: call kb_srs_upload or kb_srs_generate first"); }
+
+}  // namespace
+
+extern "C" {
+
+const char* kb_version(void) { return "keaki_b200 0.1.0 (sm_100a)"; }
+
+int32_t kb_ctx_create(int32_t device, kb_ctx** out) {
+  if (!out) return KB_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return KB_ERR_CUDA;  // no usable CUDA device: there is deliberately no CPU path
+  }
+  kb_ctx* ctx = new kb_ctx();
+  try {
+    ctx->device = device;
+    KB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    KB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) throw CudaError(std::string("device ") + prop.name + " is not sm_100-class; this library is built for sm_100a only");
+    ctx->sm_count = prop.multiProcessorCount;
+    KB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    KB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = UINT64_MAX;
+    KB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    // the generic (call-based) pairing keeps Fq12 temporaries on the per-thread stack
+    KB_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024));
+    for (auto& e : ctx->ev) KB_CUDA(cudaEventCreate(&e));
+    we_upload_consts();
+    we_init_tables(ctx);
+    KB_CUDA(cudaStreamSynchronize(ctx->stream));
+  } catch (const std::exception& e) {
+    fprintf(stderr, "kb_ctx_create: %s\n", e.what());
+    delete ctx;
+    cudaGetLastError();
+    return KB_ERR_CUDA;
+  }
+  *out = ctx;
+  return KB_OK;
+}
+
+void kb_ctx_destroy(kb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  msm_free_tables(ctx);
+  fk_free(ctx);
+  we_free(ctx);
+  if (ctx->d_srs) cudaFree(ctx->d_srs);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* kb_last_error(const kb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t kb_launch_count(const kb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+float kb_last_kernel_ms(const kb_ctx* ctx, int32_t which) { return (ctx && which >= 0 && which < KB_T_COUNT) ? ctx->last_ms[which] : -1.f; }
+uint64_t kb_srs_len(const kb_ctx* ctx) { return ctx ? ctx->srs_n : 0; }
+
+int32_t kb_srs_upload(kb_ctx* ctx, const uint32_t* g1_aff_xy, uint64_t n, const uint32_t* tau_g2_xy) {
+  KB_API_BEGIN(ctx)
+  need(tau_g2_xy != nullptr && (n == 0 || g1_aff_xy != nullptr), "kb_srs_upload: null pointer");
+  if (ctx->d_srs) { KB_CUDA(cudaFree(ctx->d_srs)); ctx->d_srs = nullptr; }
+  msm_free_tables(ctx);
+  fk_free(ctx);
+  KB_CUDA(cudaMalloc((void**)&ctx->d_srs, (size_t)(n ? n : 1) * 64));
+  ctx->srs_n = n;
+  if (n) KB_CUDA(cudaMemcpyAsync(ctx->d_srs, g1_aff_xy, n * 64, cudaMemcpyDefault, ctx->stream));
+  DevIn<uint32_t> tau2(ctx, tau_g2_xy, 32);
+  we_set_tau2(ctx, tau2);
+  KB_API_END(ctx)
+}
+
+int32_t kb_srs_generate(kb_ctx* ctx, const uint32_t* tau, uint64_t n, uint32_t* out_g1_xy, uint32_t* out_tau_g2_xy) {
+  KB_API_BEGIN(ctx)
+  need(tau != nullptr, "kb_srs_generate: null tau");
+  fk_free(ctx);
+  DevIn<uint32_t> dtau(ctx, tau, 8);
+  DevBuf<uint32_t> tau2(ctx, 32);
+  srs_generate(ctx, dtau, n, tau2);
+  we_set_tau2(ctx, tau2);
+  if (out_g1_xy && n) KB_CUDA(cudaMemcpyAsync(out_g1_xy, ctx->d_srs, n * 64, cudaMemcpyDefault, ctx->stream));
+  if (out_tau_g2_xy) KB_CUDA(cudaMemcpyAsync(out_tau_g2_xy, tau2.p, 128, cudaMemcpyDefault, ctx->stream));
+  KB_API_END(ctx)
+}
+
+int32_t kb_msm_g1(kb_ctx* ctx, const uint32_t* scalars, uint64_t first, uint64_t n, uint32_t out_xy[16], uint8_t* out_inf) {
+  KB_API_BEGIN(ctx)
+  need(out_xy != nullptr && (n == 0 || scalars != nullptr), "kb_msm_g1: null pointer");
+  need_srs(ctx);
+  if (first + n > ctx->srs_n)
+    throw ApiError(KB_ERR_POLY_TOO_LARGE, "PolynomialTooLarge(" + std::to_string(first + n) + ", " + std::to_string(ctx->srs_n) + ")");
+  DevIn<uint32_t> s(ctx, scalars, n * 8);
+  DevOut<uint32_t> o(ctx, out_xy, 16);
+  DevBuf<uint8_t> inf_scratch(ctx, 1);
+  DevOut<uint8_t> oi(ctx, out_inf, 1);
+  msm_g1(ctx, s, first, n, o, out_inf ? oi.p : inf_scratch.p);
+  o.finish(); oi.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_g1_sum(kb_ctx* ctx, const uint32_t* pts_xy, const uint8_t* inf, uint64_t n, uint32_t out_xy[16], uint8_t* out_inf) {
+  KB_API_BEGIN(ctx)
+  need(out_xy != nullptr && (n == 0 || pts_xy != nullptr), "kb_g1_sum: null pointer");
+  DevIn<uint32_t> p(ctx, pts_xy, n * 16);
+  DevIn<uint8_t> pi(ctx, inf, n);
+  DevOut<uint32_t> o(ctx, out_xy, 16);
+  DevBuf<uint8_t> inf_scratch(ctx, 1);
+  DevOut<uint8_t> oi(ctx, out_inf, 1);
+  g1_sum(ctx, p, pi, n, o, out_inf ? oi.p : inf_scratch.p);
+  o.finish(); oi.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_open_batch(kb_ctx* ctx, const uint32_t* coeffs, uint64_t d, const uint32_t* points, uint64_t m,
+                      uint32_t* proofs_xy, uint8_t* proofs_inf) {
+  KB_API_BEGIN(ctx)
+  need((d == 0 || coeffs) && (m == 0 || (points && proofs_xy && proofs_inf)), "kb_open_batch: null pointer");
+  need_srs(ctx);
+  DevIn<uint32_t> c(ctx, coeffs, d * 8), z(ctx, points, m * 8);
+  DevOut<uint32_t> o(ctx, proofs_xy, m * 16);
+  DevOut<uint8_t> oi(ctx, proofs_inf, m);
+  open_batch(ctx, c, d, z, m, o, oi);
+  o.finish(); oi.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_open_all_fk(kb_ctx* ctx, const uint32_t* coeffs, uint64_t d, uint32_t* proofs_xy, uint8_t* proofs_inf) {
+  KB_API_BEGIN(ctx)
+  need(coeffs && proofs_xy && proofs_inf && d > 0, "kb_open_all_fk: null pointer or d = 0");
+  need_srs(ctx);
+  DevIn<uint32_t> c(ctx, coeffs, d * 8);
+  DevOut<uint32_t> o(ctx, proofs_xy, d * 16);
+  DevOut<uint8_t> oi(ctx, proofs_inf, d);
+  open_all_fk(ctx, c, d, o, oi);
+  o.finish(); oi.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_fr_ntt(kb_ctx* ctx, uint32_t* data, uint64_t n, int32_t inverse) {
+  KB_API_BEGIN(ctx)
+  need(data != nullptr && n > 0, "kb_fr_ntt: null pointer or n = 0");
+  if (is_device_ptr(data)) {
+    fr_ntt(ctx, data, n, inverse != 0);
+  } else {
+    DevBuf<uint32_t> d(ctx, n * 8);
+    KB_CUDA(cudaMemcpyAsync(d.p, data, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    fr_ntt(ctx, d.p, n, inverse != 0);
+    KB_CUDA(cudaMemcpyAsync(data, d.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  KB_API_END(ctx)
+}
+
+int32_t kb_encrypt_batch(kb_ctx* ctx, const uint32_t com_xy[16], uint8_t com_inf, const uint32_t* points, const uint32_t* values,
+                         const uint32_t* r, const uint8_t* msgs, const uint64_t* msg_off, uint64_t n,
+                         uint32_t* ct_g2_xy, uint8_t* ct_inf, uint8_t* msg_ct) {
+  KB_API_BEGIN(ctx)
+  need(com_xy != nullptr, "kb_encrypt_batch: null commitment");
+  need(n == 0 || (points && values && r && msg_off && ct_g2_xy && ct_inf), "kb_encrypt_batch: null pointer");
+  need_srs(ctx);
+  uint32_t com_host[16];
+  KB_CUDA(cudaMemcpy(com_host, com_xy, 64, cudaMemcpyDefault));
+  uint64_t total = 0;
+  if (n) KB_CUDA(cudaMemcpy(&total, msg_off + n, 8, cudaMemcpyDefault));
+  need(total == 0 || (msgs && msg_ct), "kb_encrypt_batch: null message buffer");
+  DevIn<uint32_t> dp(ctx, points, n * 8), dv(ctx, values, n * 8), dr(ctx, r, n * 8);
+  DevIn<uint8_t> dm(ctx, msgs, total);
+  DevIn<uint64_t> doff(ctx, msg_off, n + 1);
+  DevOut<uint32_t> oc(ctx, ct_g2_xy, n * 32);
+  DevOut<uint8_t> oi(ctx, ct_inf, n), om(ctx, msg_ct, total);
+  encrypt_batch(ctx, com_host, com_inf, dp, dv, dr, dm, doff, n, oc, oi, om);
+  oc.finish(); oi.finish(); om.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_decrypt_batch(kb_ctx* ctx, const uint32_t* proofs_xy, const uint8_t* proofs_inf, const uint32_t* ct_g2_xy,
+                         const uint8_t* ct_inf, const uint8_t* msg_ct, const uint64_t* msg_off, uint64_t n, uint8_t* msgs_out) {
+  KB_API_BEGIN(ctx)
+  need(n == 0 || (proofs_xy && ct_g2_xy && msg_off), "kb_decrypt_batch: null pointer");
+  uint64_t total = 0;
+  if (n) KB_CUDA(cudaMemcpy(&total, msg_off + n, 8, cudaMemcpyDefault));
+  need(total == 0 || (msg_ct && msgs_out), "kb_decrypt_batch: null message buffer");
+  DevIn<uint32_t> dp(ctx, proofs_xy, n * 16), dc(ctx, ct_g2_xy, n * 32);
+  DevIn<uint8_t> dpi(ctx, proofs_inf, n), dci(ctx, ct_inf, n), dm(ctx, msg_ct, total);
+  DevIn<uint64_t> doff(ctx, msg_off, n + 1);
+  DevOut<uint8_t> om(ctx, msgs_out, total);
+  decrypt_batch(ctx, dp, dpi, dc, dci, dm, doff, n, om);
+  om.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_pairing_batch(kb_ctx* ctx, const uint32_t* g1_xy, const uint8_t* g1_inf, const uint32_t* g2_xy, const uint8_t* g2_inf,
+                         uint64_t n, uint8_t* gt_bytes) {
+  KB_API_BEGIN(ctx)
+  need(n == 0 || (g1_xy && g2_xy && gt_bytes), "kb_pairing_batch: null pointer");
+  DevIn<uint32_t> a(ctx, g1_xy, n * 16), b(ctx, g2_xy, n * 32);
+  DevIn<uint8_t> ai(ctx, g1_inf, n), bi(ctx, g2_inf, n);
+  DevOut<uint8_t> o(ctx, gt_bytes, n * 384);
+  pairing_batch(ctx, a, ai, b, bi, n, o);
+  o.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_verify_batch(kb_ctx* ctx, const uint32_t* com_xy, const uint8_t* com_inf, const uint32_t* points, const uint32_t* values,
+                        const uint32_t* proofs_xy, const uint8_t* proofs_inf, uint64_t n, uint8_t* ok) {
+  KB_API_BEGIN(ctx)
+  need(n == 0 || (com_xy && points && values && proofs_xy && ok), "kb_verify_batch: null pointer");
+  need_srs(ctx);
+  DevIn<uint32_t> c(ctx, com_xy, n * 16), z(ctx, points, n * 8), v(ctx, values, n * 8), p(ctx, proofs_xy, n * 16);
+  DevIn<uint8_t> ci(ctx, com_inf, n), pi(ctx, proofs_inf, n);
+  DevOut<uint8_t> o(ctx, ok, n);
+  verify_batch(ctx, c, ci, z, v, p, pi, n, o);
+  o.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_debug_fp_op(kb_ctx* ctx, int32_t field, int32_t op, const uint32_t* a, const uint32_t* b, uint32_t* out, uint64_t n) {
+  KB_API_BEGIN(ctx)
+  need(a && b && out, "kb_debug_fp_op: null pointer");
+  DevIn<uint32_t> da(ctx, a, n * 8), db(ctx, b, n * 8);
+  DevOut<uint32_t> o(ctx, out, n * 8);
+  debug_fp_op(ctx, field, op, da, db, o, n);
+  o.finish();
+  KB_API_END(ctx)
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// Library-internal context and launch helpers (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/keaki_b200.h"
+#include "pairing.cuh"
+
+namespace kb {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct ApiError : std::runtime_error {
+  int32_t code;
+  ApiError(int32_t c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define KB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
+  throw kb::CudaError(std::string(#x) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); } while (0)
+
+// Fixed-base tables for the MSM over the SRS: tab[w * n + i] = 2^(c w) * g1[i], affine.
+struct MsmTable { int c = 0, nwin = 0; uint64_t n = 0; uint32_t* d = nullptr; };
+
+enum { KB_T_TOTAL = 0, KB_T_MSM_ACC = 1, KB_T_PAIRING = 2, KB_T_ENCRYPT = 3, KB_T_COUNT = 4 };
+
+}  // namespace kb
+
+struct kb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 148;
+
+  // SRS (affine, Montgomery), resident for the life of the context
+  uint32_t* d_srs = nullptr;
+  uint64_t srs_n = 0;
+  std::vector<kb::MsmTable> msm_tabs;
+
+  // fixed-base tables for witness encryption (8-bit windows, 32 windows x 255 entries)
+  uint32_t* d_g2_tab = nullptr;      // d * 2^(8w) * G2, affine (32 limbs each)
+  uint32_t* d_tau2_tab = nullptr;    // d * 2^(8w) * tau_2
+  uint32_t* d_gt_tab = nullptr;      // e(G1, G2)^(d 2^(8w)), Fq12 Montgomery (96 limbs each)
+  uint32_t* d_com_tab = nullptr;     // e(com, G2)^(d 2^(8w)) for the cached commitment
+  uint32_t com_cached[17] = {0};     // xy + inf flag of the commitment the table was built for
+  bool com_tab_valid = false;
+
+  // FK open-all cache: hat_s = DFT_2d(reversed SRS prefix) per d
+  struct FkCache { uint64_t d = 0; uint32_t* d_hat_s = nullptr; };
+  std::vector<FkCache> fk_cache;
+
+  cudaEvent_t ev[2 * kb::KB_T_COUNT] = {};
+  float last_ms[kb::KB_T_COUNT] = {-1.f, -1.f, -1.f, -1.f};
+};
+
+namespace kb {
+
+// Stream-ordered scratch buffer (pool allocator: no cudaMalloc on the hot path after warm-up).
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  cudaStream_t s;
+  DevBuf(kb_ctx* ctx, size_t count) : s(ctx->stream) {
+    if (count) KB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), s));
+  }
+  ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  operator T*() const { return p; }
+};
+
+inline bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Input staged on the device: either the caller's device pointer, or an async copy of host memory.
+template <class T>
+struct DevIn {
+  const T* p = nullptr;
+  T* owned = nullptr;
+  cudaStream_t s;
+  DevIn(kb_ctx* ctx, const T* src, size_t count) : s(ctx->stream) {
+    if (!src || !count) return;
+    if (is_device_ptr(src)) { p = src; return; }
+    KB_CUDA(cudaMallocAsync((void**)&owned, count * sizeof(T), s));
+    KB_CUDA(cudaMemcpyAsync(owned, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    p = owned;
+  }
+  ~DevIn() { if (owned) cudaFreeAsync(owned, s); }
+  DevIn(const DevIn&) = delete;
+  DevIn& operator=(const DevIn&) = delete;
+  operator const T*() const { return p; }
+};
+
+// Output: device scratch copied back to host at the end, or the caller's device pointer directly.
+template <class T>
+struct DevOut {
+  T* p = nullptr;
+  T* owned = nullptr;
+  T* host = nullptr;
+  size_t count;
+  cudaStream_t s;
+  DevOut(kb_ctx* ctx, T* dst, size_t count_) : count(count_), s(ctx->stream) {
+    if (!dst || !count) return;
+    if (is_device_ptr(dst)) { p = dst; return; }
+    KB_CUDA(cudaMallocAsync((void**)&owned, count * sizeof(T), s));
+    p = owned; host = dst;
+  }
+  void finish() { if (owned && host) KB_CUDA(cudaMemcpyAsync(host, owned, count * sizeof(T), cudaMemcpyDeviceToHost, s)); }
+  ~DevOut() { if (owned) cudaFreeAsync(owned, s); }
+  DevOut(const DevOut&) = delete;
+  DevOut& operator=(const DevOut&) = delete;
+  operator T*() const { return p; }
+};
+
+#define KB_LAUNCH(ctx, kernel, grid, block, smem, ...) do { \
+  kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+  (ctx)->launches++; KB_CUDA(cudaGetLastError()); } while (0)
+
+inline void timer_start(kb_ctx* c, int which) { KB_CUDA(cudaEventRecord(c->ev[2 * which], c->stream)); }
+inline void timer_stop(kb_ctx* c, int which) { KB_CUDA(cudaEventRecord(c->ev[2 * which + 1], c->stream)); c->last_ms[which] = -2.f; }
+inline void timers_collect(kb_ctx* c) {
+  for (int i = 0; i < KB_T_COUNT; i++)
+    if (c->last_ms[i] == -2.f) { float ms = -1.f; if (cudaEventElapsedTime(&ms, c->ev[2 * i], c->ev[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); ms = -1.f; } c->last_ms[i] = ms; }
+}
+
+inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// device-side loaders shared by the kernels
+__device__ __forceinline__ Fq2 ld_fq2(const uint32_t* p) { Fq2 r; r.c0 = fp_load<FqParams>(p); r.c1 = fp_load<FqParams>(p + 8); return r; }
+__device__ __forceinline__ void st_fq2(uint32_t* p, const Fq2& a) { fp_store<FqParams>(p, a.c0); fp_store<FqParams>(p + 8, a.c1); }
+__device__ __forceinline__ G1Affine ld_g1(const uint32_t* p) { G1Affine r; r.x = fp_load<FqParams>(p); r.y = fp_load<FqParams>(p + 8); return r; }
+__device__ __forceinline__ void st_g1(uint32_t* p, const G1Affine& a) { fp_store<FqParams>(p, a.x); fp_store<FqParams>(p + 8, a.y); }
+__device__ __forceinline__ G2Affine ld_g2(const uint32_t* p) { G2Affine r; r.x = ld_fq2(p); r.y = ld_fq2(p + 16); return r; }
+__device__ __forceinline__ void st_g2(uint32_t* p, const G2Affine& a) { st_fq2(p, a.x); st_fq2(p + 16, a.y); }
+__device__ __forceinline__ G1 ld_g1x(const uint32_t* p) { G1 r; r.x = fp_load<FqParams>(p); r.y = fp_load<FqParams>(p + 8); r.zz = fp_load<FqParams>(p + 16); r.zzz = fp_load<FqParams>(p + 24); return r; }
+__device__ __forceinline__ void st_g1x(uint32_t* p, const G1& a) { fp_store<FqParams>(p, a.x); fp_store<FqParams>(p + 8, a.y); fp_store<FqParams>(p + 16, a.zz); fp_store<FqParams>(p + 24, a.zzz); }
+__device__ __forceinline__ Fq12 ld_fq12(const uint32_t* p) {
+  Fq12 r;
+  r.c0.c0 = ld_fq2(p); r.c0.c1 = ld_fq2(p + 16); r.c0.c2 = ld_fq2(p + 32);
+  r.c1.c0 = ld_fq2(p + 48); r.c1.c1 = ld_fq2(p + 64); r.c1.c2 = ld_fq2(p + 80);
+  return r;
+}
+__device__ __forceinline__ void st_fq12(uint32_t* p, const Fq12& a) {
+  st_fq2(p, a.c0.c0); st_fq2(p + 16, a.c0.c1); st_fq2(p + 32, a.c0.c2);
+  st_fq2(p + 48, a.c1.c0); st_fq2(p + 64, a.c1.c1); st_fq2(p + 80, a.c1.c2);
+}
+
+// ---- entry points implemented per translation unit (msm.cu, we.cu, poly.cu) ----
+void msm_g1(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t first, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf);
+void g1_sum(kb_ctx* ctx, const uint32_t* d_pts, const uint8_t* d_inf, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf);
+void g1_xyzz_sum_to_affine(kb_ctx* ctx, uint32_t* d_xyzz /* n*32, destroyed */, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf);
+void msm_free_tables(kb_ctx* ctx);
+void launch_msm_accumulate(kb_ctx* ctx, const uint32_t* tab, uint64_t tab_n, uint64_t first, const uint32_t* offsets,
+                           const uint32_t* entries, uint32_t nb, uint32_t* buckets);
+void srs_generate(kb_ctx* ctx, const uint32_t* d_tau, uint64_t n, uint32_t* d_tau_g2_out);
+void we_init_tables(kb_ctx* ctx);                       // G2 generator + gT tables (ctx creation)
+void we_set_tau2(kb_ctx* ctx, const uint32_t* d_tau2);  // tau_2 table (SRS upload)
+void we_free(kb_ctx* ctx);
+void we_upload_consts();
+void pairing_batch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
+                   uint64_t n, uint8_t* d_gt_bytes);
+void decrypt_batch(kb_ctx* ctx, const uint32_t* d_proofs, const uint8_t* d_pinf, const uint32_t* d_ct, const uint8_t* d_cinf,
+                   const uint8_t* d_msg_ct, const uint64_t* d_off, uint64_t n, uint8_t* d_out);
+void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const uint32_t* d_points, const uint32_t* d_values,
+                   const uint32_t* d_r, const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n,
+                   uint32_t* d_ct, uint8_t* d_ct_inf, uint8_t* d_msg_ct);
+void verify_batch(kb_ctx* ctx, const uint32_t* d_com, const uint8_t* d_com_inf, const uint32_t* d_points, const uint32_t* d_values,
+                  const uint32_t* d_proofs, const uint8_t* d_pinf, uint64_t n, uint8_t* d_ok);
+void fr_ntt(kb_ctx* ctx, uint32_t* d_data, uint64_t n, bool inverse);
+void open_batch(kb_ctx* ctx, const uint32_t* d_coeffs, uint64_t d, const uint32_t* d_points, uint64_t m,
+                uint32_t* d_proofs, uint8_t* d_inf);
+void open_all_fk(kb_ctx* ctx, const uint32_t* d_coeffs, uint64_t d, uint32_t* d_proofs, uint8_t* d_inf);
+void fk_free(kb_ctx* ctx);
+void debug_fp_op(kb_ctx* ctx, int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, uint64_t n);
+
+}  // namespace kb

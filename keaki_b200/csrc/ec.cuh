@@ -38,7 +38,7 @@ KB_HD XYZZ<F> neg(const XYZZ<F>& a) { XYZZ<F> r = a; r.y = -a.y; return r; }
 
 // dbl-2008-s-1
 template <class F>
-KB_HD XYZZ<F> ec_dbl(const XYZZ<F>& p) {
+KB_FN XYZZ<F> ec_dbl(const XYZZ<F>& p) {
   if (p.is_inf()) return p;
   F u = dbl(p.y), v = sqr(u), w = u * v, s = p.x * v;
   F x2 = sqr(p.x);
@@ -53,7 +53,7 @@ KB_HD XYZZ<F> ec_dbl(const XYZZ<F>& p) {
 
 // doubling of an affine point (mdbl-2008-s-1)
 template <class F>
-KB_HD XYZZ<F> ec_dbl_affine(const Affine<F>& p) {
+KB_FN XYZZ<F> ec_dbl_affine(const Affine<F>& p) {
   if (p.is_inf()) return XYZZ<F>::infinity();
   F u = dbl(p.y), v = sqr(u), w = u * v, s = p.x * v;
   F x2 = sqr(p.x);
@@ -68,7 +68,7 @@ KB_HD XYZZ<F> ec_dbl_affine(const Affine<F>& p) {
 
 // madd-2008-s with the exceptional cases (P = +-Q, either operand at infinity) handled.
 template <class F>
-KB_HD XYZZ<F> ec_add_mixed(const XYZZ<F>& p, const Affine<F>& q) {
+KB_FN XYZZ<F> ec_add_mixed(const XYZZ<F>& p, const Affine<F>& q) {
   if (q.is_inf()) return p;
   if (p.is_inf()) return to_xyzz(q);
   F u2 = q.x * p.zz, s2 = q.y * p.zzz;
@@ -88,7 +88,7 @@ KB_HD XYZZ<F> ec_add_mixed(const XYZZ<F>& p, const Affine<F>& q) {
 
 // add-2008-s
 template <class F>
-KB_HD XYZZ<F> ec_add(const XYZZ<F>& p, const XYZZ<F>& q) {
+KB_FN XYZZ<F> ec_add(const XYZZ<F>& p, const XYZZ<F>& q) {
   if (q.is_inf()) return p;
   if (p.is_inf()) return q;
   F u1 = p.x * q.zz, u2 = q.x * p.zz, s1 = p.y * q.zzz, s2 = q.y * p.zzz;
@@ -108,7 +108,7 @@ KB_HD XYZZ<F> ec_add(const XYZZ<F>& p, const XYZZ<F>& q) {
 
 // Affine normalisation with a single inversion.
 template <class F>
-KB_HD Affine<F> to_affine(const XYZZ<F>& p) {
+KB_FN Affine<F> to_affine(const XYZZ<F>& p) {
   if (p.is_inf()) return Affine<F>::infinity();
   F i = inv(p.zz * p.zzz);
   Affine<F> r;

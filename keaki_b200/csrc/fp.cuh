@@ -19,14 +19,24 @@
 #pragma once
 #include <stdint.h>
 
+// Inlining policy.  ptxas time explodes when the ~200-instruction multiplier is force-inlined into
+// whole curve / tower formulas, so by default (cold code: table builds, reductions, the generic
+// pairing) KB_FN functions are real calls with operands passed by value in registers.  A hot
+// kernel lives in its own translation unit and defines KB_INLINE_ALL before including this file.
 #if defined(__CUDACC__)
 #define KB_HD __host__ __device__ __forceinline__
 #define KB_D __device__ __forceinline__
-#define KB_HD_NOINLINE __host__ __device__ __noinline__
+#define KB_HD_NOINLINE inline __host__ __device__ __noinline__
+#ifdef KB_INLINE_ALL
+#define KB_FN __host__ __device__ __forceinline__
+#else
+#define KB_FN inline __host__ __device__ __noinline__
+#endif
 #else
 #define KB_HD inline
 #define KB_D inline
-#define KB_HD_NOINLINE
+#define KB_HD_NOINLINE inline
+#define KB_FN inline
 #endif
 
 namespace kb {
@@ -217,7 +227,7 @@ KB_HD Fp<P> fp_dbl(const Fp<P>& a) { return fp_add<P>(a, a); }
 
 // Montgomery product a * b * R^{-1} mod p, fully reduced.
 template <class P>
-KB_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+KB_HD Fp<P> fp_mul_inl(const Fp<P>& a, const Fp<P>& b) {
   uint32_t ev[8], od[8];
   mont_step<P, true>(ev, od, a.v, b.v[0]);
   mont_step<P, false>(od, ev, a.v, b.v[1]);
@@ -238,7 +248,9 @@ KB_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 }
 
 template <class P>
-KB_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul<P>(a, a); }
+KB_FN Fp<P> fp_mul(Fp<P> a, Fp<P> b) { return fp_mul_inl<P>(a, b); }
+template <class P>
+KB_FN Fp<P> fp_sqr(Fp<P> a) { return fp_mul_inl<P>(a, a); }
 
 // Montgomery form -> canonical integer (one Montgomery product by 1)
 template <class P>

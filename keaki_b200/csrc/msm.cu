@@ -1,0 +1,312 @@
+// G1 multi-scalar multiplication over the resident SRS — the kernel behind `commit`
+// (src/kzg.rs:89-101: VariableBaseMSM::msm_unchecked(&setup.g1_aff, p)) and `open` (src/kzg.rs:123).
+//
+// B200-first design:
+//  * The bases are the fixed SRS, so HBM capacity is traded for work: for a window width c the
+//    table tab[w][i] = 2^(c w) * g1[i] is built once per SRS (affine, 64 B per entry).  All
+//    ceil(255/c) windows of all points then fall into ONE set of 2^(c-1) signed-digit buckets:
+//    one bucket reduction instead of one per window and no final Horner doubling chain.
+//  * Scalars are taken out of Montgomery form and recoded into signed c-bit digits on the fly
+//    (never stored); entries (point, window, sign) are counting-sorted by bucket with global
+//    atomics; one thread owns one bucket and accumulates its entries with XYZZ mixed additions,
+//    prefetching the next base while the current addition runs.
+//  * Bucket reduction: segments of 8 buckets by running sums, segment weight by a short
+//    double-and-add, then a tree sum.
+// The result leaves as canonical affine coordinates, so it is bit-identical to arkworks' for any
+// summation order.
+#include "ctx.cuh"
+#include "msm_digits.cuh"
+#include "consts_gen.cuh"
+
+namespace kb {
+
+static constexpr int MSM_SEG = 8;  // buckets per thread in the reduction
+
+// ------------------------------------------------------------------------------------------
+// window choice and table build
+// ------------------------------------------------------------------------------------------
+static int msm_choose_c(uint64_t end) {
+  if (end <= 256) return 8;
+  if (end <= (1ull << 13)) return 12;
+  if (end <= (1ull << 17)) return 16;
+  return 20;
+}
+static uint64_t msm_table_cap(int c, uint64_t srs_n) {
+  uint64_t cap = c == 8 ? 256 : c == 12 ? (1ull << 13) : c == 16 ? (1ull << 17) : srs_n;
+  return cap < srs_n ? cap : srs_n;
+}
+
+__global__ void __launch_bounds__(128) msm_build_table_kernel(const uint32_t* __restrict__ srs, uint64_t n, int c, int nwin,
+                                                              uint32_t* __restrict__ tab) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = ld_g1(srs + 16 * i);
+  st_g1(tab + 16 * i, p);
+  G1 acc = to_xyzz(p);
+  for (int w = 1; w < nwin; w++) {
+    for (int k = 0; k < c; k++) acc = ec_dbl(acc);
+    st_g1(tab + 16 * ((uint64_t)w * n + i), to_affine(acc));
+  }
+}
+
+static const MsmTable& msm_get_table(kb_ctx* ctx, int c) {
+  for (auto& t : ctx->msm_tabs) if (t.c == c) return t;
+  MsmTable t;
+  t.c = c; t.nwin = msm_num_windows(c); t.n = msm_table_cap(c, ctx->srs_n);
+  KB_CUDA(cudaMalloc((void**)&t.d, (size_t)t.nwin * t.n * 64));
+  KB_LAUNCH(ctx, msm_build_table_kernel, cdiv(t.n, 128), 128, 0, ctx->d_srs, t.n, c, t.nwin, t.d);
+  ctx->msm_tabs.push_back(t);
+  return ctx->msm_tabs.back();
+}
+
+void msm_free_tables(kb_ctx* ctx) {
+  for (auto& t : ctx->msm_tabs) if (t.d) cudaFree(t.d);
+  ctx->msm_tabs.clear();
+}
+
+// ------------------------------------------------------------------------------------------
+// recode + count, scan, scatter
+// ------------------------------------------------------------------------------------------
+// entry packing: bit 31 = negate, bits 26..30 = window, bits 0..25 = point index within the call
+__device__ __forceinline__ void msm_load_digits(const uint32_t* scalars, uint64_t i, int c, int nwin, int32_t* dg) {
+  Fr s = fp_load<FrParams>(scalars + 8 * i);
+  Fr k = fp_from_mont<FrParams>(s);
+  msm_signed_digits(k.v, c, nwin, dg);
+}
+
+__global__ void __launch_bounds__(256) msm_count_kernel(const uint32_t* __restrict__ scalars, uint64_t n, int c, int nwin,
+                                                        uint32_t* __restrict__ counts) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t dg[32];
+  msm_load_digits(scalars, i, c, nwin, dg);
+  for (int w = 0; w < nwin; w++) {
+    int32_t d = dg[w];
+    if (d != 0) atomicAdd(&counts[(d < 0 ? -d : d) - 1], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* __restrict__ scalars, uint64_t n, int c, int nwin,
+                                                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t dg[32];
+  msm_load_digits(scalars, i, c, nwin, dg);
+  for (int w = 0; w < nwin; w++) {
+    int32_t d = dg[w];
+    if (d == 0) continue;
+    uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
+    uint32_t pos = atomicAdd(&cursor[b], 1u);
+    entries[pos] = (uint32_t)i | ((uint32_t)w << 26) | (d < 0 ? 0x80000000u : 0u);
+  }
+}
+
+// Exclusive scan of `n` u32 counts: block-local scan (1024 per block) + serial scan of block sums.
+__global__ void __launch_bounds__(256) scan_local_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                         uint32_t* __restrict__ block_sums, uint32_t n) {
+  __shared__ uint32_t warp_tot[8];
+  uint32_t base = blockIdx.x * 1024u + threadIdx.x * 4u;
+  uint32_t v[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) v[k] = base + k < n ? in[base + k] : 0u;
+  uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+  uint32_t incl = tsum;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int k = 0; k < wid; k++) woff += warp_tot[k];
+  uint32_t excl = woff + incl - tsum;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { if (base + k < n) out[base + k] = excl; excl += v[k]; }
+  if (threadIdx.x == 255) block_sums[blockIdx.x] = woff + incl;
+}
+__global__ void scan_sums_kernel(uint32_t* block_sums, uint32_t nblocks) {
+  // single thread: nblocks <= 2^(c-1)/1024 <= 512
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < nblocks; i++) { uint32_t t = block_sums[i]; block_sums[i] = acc; acc += t; }
+    block_sums[nblocks] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) scan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ block_sums,
+                                                       uint32_t* __restrict__ cursor, uint32_t n, uint32_t nblocks) {
+  uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i < n) { uint32_t v = out[i] + block_sums[i >> 10]; out[i] = v; cursor[i] = v; }
+  if (i == n) out[n] = block_sums[nblocks];  // total
+}
+
+// ------------------------------------------------------------------------------------------
+// bucket reduction: sum_b (b+1) * B_b
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) msm_reduce_seg_kernel(const uint32_t* __restrict__ buckets, uint32_t nb,
+                                                             uint32_t* __restrict__ partial) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t lo = t * MSM_SEG;
+  if (lo >= nb) return;
+  uint32_t hi = lo + MSM_SEG < nb ? lo + MSM_SEG : nb;
+  G1 run = G1::infinity(), sum = G1::infinity();
+  for (uint32_t j = hi; j-- > lo;) {
+    run = ec_add(run, ld_g1x(buckets + 32 * (uint64_t)j));
+    sum = ec_add(sum, run);
+  }
+  // sum = sum_j (j - lo + 1) B_j ; add lo * run
+  if (lo != 0 && !run.is_inf()) {
+    G1 m = G1::infinity();
+    for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
+      m = ec_dbl(m);
+      if ((lo >> bit) & 1u) m = ec_add(m, run);
+    }
+    sum = ec_add(sum, m);
+  }
+  st_g1x(partial + 32 * (uint64_t)t, sum);
+}
+
+// tree sum of XYZZ points: each block folds up to 256 * per inputs into one output
+__global__ void __launch_bounds__(256) g1_tree_sum_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t per,
+                                                          uint32_t* __restrict__ out) {
+  __shared__ uint32_t sm[128 * 32];
+  uint64_t base = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * per;
+  G1 acc = G1::infinity();
+  for (uint32_t k = 0; k < per; k++) if (base + k < n) acc = ec_add(acc, ld_g1x(in + 32 * (base + k)));
+  for (int half = 128; half >= 1; half >>= 1) {
+    if (threadIdx.x >= half && threadIdx.x < 2 * half) {
+      uint32_t* s = sm + 32 * (threadIdx.x - half);
+#pragma unroll
+      for (int q = 0; q < 8; q++) { s[q] = acc.x.v[q]; s[8 + q] = acc.y.v[q]; s[16 + q] = acc.zz.v[q]; s[24 + q] = acc.zzz.v[q]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < half) {
+      const uint32_t* s = sm + 32 * threadIdx.x;
+      G1 o;
+#pragma unroll
+      for (int q = 0; q < 8; q++) { o.x.v[q] = s[q]; o.y.v[q] = s[8 + q]; o.zz.v[q] = s[16 + q]; o.zzz.v[q] = s[24 + q]; }
+      acc = ec_add(acc, o);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_g1x(out + 32 * (uint64_t)blockIdx.x, acc);
+}
+
+__global__ void g1_finalize_kernel(const uint32_t* __restrict__ xyzz, uint32_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  G1 p = ld_g1x(xyzz);
+  G1Affine a = to_affine(p);
+  st_g1(out_xy, a);
+  if (out_inf) *out_inf = p.is_inf() ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) g1_affine_to_xyzz_kernel(const uint32_t* __restrict__ pts, const uint8_t* __restrict__ inf,
+                                                                uint64_t n, uint32_t* __restrict__ out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine a = ld_g1(pts + 16 * i);
+  if (inf && inf[i]) a = G1Affine::infinity();
+  st_g1x(out + 32 * i, to_xyzz(a));
+}
+
+// Sums n XYZZ points (array is consumed) and writes the affine result.
+void g1_xyzz_sum_to_affine(kb_ctx* ctx, uint32_t* d_xyzz, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
+  if (n == 0) {
+    KB_CUDA(cudaMemsetAsync(d_out_xy, 0, 64, ctx->stream));
+    if (d_out_inf) KB_CUDA(cudaMemsetAsync(d_out_inf, 1, 1, ctx->stream));
+    return;
+  }
+  uint64_t cur_n = n;
+  DevBuf<uint32_t> tmp(ctx, 32 * (size_t)cdiv(n, 256));
+  uint32_t* src = d_xyzz;
+  uint32_t* dst = tmp;
+  while (cur_n > 1) {
+    // keep blocks full when there is a lot to fold, but never fewer than needed
+    uint32_t per = cur_n >= (1u << 16) ? 4 : 1;
+    unsigned blocks = cdiv(cur_n, 256ull * per);
+    KB_LAUNCH(ctx, g1_tree_sum_kernel, blocks, 256, 0, src, cur_n, per, dst);
+    cur_n = blocks;
+    uint32_t* t = src; src = dst; dst = t;
+  }
+  KB_LAUNCH(ctx, g1_finalize_kernel, 1, 32, 0, src, d_out_xy, d_out_inf);
+}
+
+void g1_sum(kb_ctx* ctx, const uint32_t* d_pts, const uint8_t* d_inf, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
+  DevBuf<uint32_t> x(ctx, 32 * (size_t)(n ? n : 1));
+  if (n) KB_LAUNCH(ctx, g1_affine_to_xyzz_kernel, cdiv(n, 256), 256, 0, d_pts, d_inf, n, x);
+  g1_xyzz_sum_to_affine(ctx, x, n, d_out_xy, d_out_inf);
+}
+
+// ------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------
+void msm_g1(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t first, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
+  if (n == 0) {
+    KB_CUDA(cudaMemsetAsync(d_out_xy, 0, 64, ctx->stream));
+    if (d_out_inf) KB_CUDA(cudaMemsetAsync(d_out_inf, 1, 1, ctx->stream));
+    return;
+  }
+  if (n > (1ull << 26)) throw ApiError(KB_ERR_ARG, "kb_msm_g1: more than 2^26 points in one call");
+  const int c = msm_choose_c(first + n);
+  const MsmTable& tab = msm_get_table(ctx, c);
+  const uint32_t nb = 1u << (c - 1);
+  const uint32_t nblk = cdiv(nb, 1024);
+
+  DevBuf<uint32_t> counts(ctx, nb);
+  DevBuf<uint32_t> offsets(ctx, nb + 1);
+  DevBuf<uint32_t> cursor(ctx, nb);
+  DevBuf<uint32_t> bsums(ctx, nblk + 1);
+  DevBuf<uint32_t> entries(ctx, (size_t)n * tab.nwin);
+  DevBuf<uint32_t> buckets(ctx, 32 * (size_t)nb);
+  const uint32_t nseg = cdiv(nb, MSM_SEG);
+  DevBuf<uint32_t> partial(ctx, 32 * (size_t)nseg);
+
+  KB_CUDA(cudaMemsetAsync(counts, 0, nb * sizeof(uint32_t), ctx->stream));
+  KB_LAUNCH(ctx, msm_count_kernel, cdiv(n, 256), 256, 0, d_scalars, n, c, tab.nwin, counts);
+  KB_LAUNCH(ctx, scan_local_kernel, nblk, 256, 0, counts, offsets, bsums, nb);
+  KB_LAUNCH(ctx, scan_sums_kernel, 1, 32, 0, bsums, nblk);
+  KB_LAUNCH(ctx, scan_add_kernel, cdiv(nb + 1, 256), 256, 0, offsets, bsums, cursor, nb, nblk);
+  KB_LAUNCH(ctx, msm_scatter_kernel, cdiv(n, 256), 256, 0, d_scalars, n, c, tab.nwin, cursor, entries);
+  timer_start(ctx, KB_T_MSM_ACC);
+  launch_msm_accumulate(ctx, tab.d, tab.n, first, offsets, entries, nb, buckets);
+  timer_stop(ctx, KB_T_MSM_ACC);
+  KB_LAUNCH(ctx, msm_reduce_seg_kernel, cdiv(nseg, 128), 128, 0, buckets, nb, partial);
+  g1_xyzz_sum_to_affine(ctx, partial, nseg, d_out_xy, d_out_inf);
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic SRS: g1[i] = tau^i * G1 (harness; `KZGSetup::setup`, src/kzg.rs:55-70)
+// ------------------------------------------------------------------------------------------
+// Each thread owns a run of consecutive powers: tau^(t*RUN) by square-and-multiply, then RUN
+// scalar multiplications of the generator.
+__global__ void __launch_bounds__(128) srs_generate_kernel(const uint32_t* __restrict__ tau_m, uint64_t n, uint32_t* __restrict__ out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr tau = fp_load<FrParams>(tau_m);
+  // tau^i
+  Fr acc = Fr::one(), base = tau;
+  for (uint64_t e = i; e; e >>= 1) { if (e & 1) acc = acc * base; base = sqr(base); }
+  Fr k = fp_from_mont<FrParams>(acc);
+  G1Affine g;
+  g.x = Fq::one();
+  g.y = Fq::one() + Fq::one();
+  st_g1(out + 16 * i, to_affine(ec_mul(to_xyzz(g), k.v)));
+}
+
+__global__ void srs_tau_g2_kernel(const uint32_t* __restrict__ tau_m, const uint32_t* __restrict__ g2_gen, uint32_t* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Fr k = fp_from_mont<FrParams>(fp_load<FrParams>(tau_m));
+  G2Affine g = ld_g2(g2_gen);
+  st_g2(out, to_affine(ec_mul(to_xyzz(g), k.v)));
+}
+
+void srs_generate(kb_ctx* ctx, const uint32_t* d_tau, uint64_t n, uint32_t* d_tau_g2_out) {
+  if (ctx->d_srs) { KB_CUDA(cudaFree(ctx->d_srs)); ctx->d_srs = nullptr; }
+  msm_free_tables(ctx);
+  KB_CUDA(cudaMalloc((void**)&ctx->d_srs, (size_t)(n ? n : 1) * 64));
+  ctx->srs_n = n;
+  if (n) KB_LAUNCH(ctx, srs_generate_kernel, cdiv(n, 128), 128, 0, d_tau, n, ctx->d_srs);
+  DevBuf<uint32_t> gen(ctx, 32);
+  KB_CUDA(cudaMemcpyAsync(gen, consts::G2_GEN, 128, cudaMemcpyHostToDevice, ctx->stream));
+  KB_LAUNCH(ctx, srs_tau_g2_kernel, 1, 32, 0, d_tau, gen, d_tau_g2_out);
+}
+
+}  // namespace kb

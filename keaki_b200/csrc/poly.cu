@@ -1,0 +1,254 @@
+// Polynomial layer: radix-2 NTT over Fr (src/vec.rs:37, src/kzg.rs:185), quotient polynomials for
+// `open` (src/kzg.rs:104-124) and the FK23 all-openings algorithm `open_fk` (src/kzg.rs:157-203).
+//
+// open_fk data flow here (same mathematics as the reference, fewer group operations):
+//   hat_s = DFT_2d(s), s = reversed SRS prefix || d x infinity, depends only on (SRS, d): computed
+//           once and cached in the context (the reference recomputes it on every call, :182);
+//   hat_a = DFT_2d(0^d || p) over Fr; hat_h[i] = (hat_a[i] / 2d) * hat_s[i]   (:185-191, iDFT scale folded in);
+//   h = first d entries of DFT^-1_2d(hat_h) (unscaled); proofs = DFT_d(h)            (:194-200).
+// G1 transforms use XYZZ points and scalar-multiplication butterflies, skipping unit twiddles.
+#include "ctx.cuh"
+#include "consts_gen.cuh"
+
+namespace kb {
+
+static int log2_exact(uint64_t n) {
+  if (n == 0 || (n & (n - 1))) return -1;
+  int k = 0;
+  while ((1ull << k) < n) k++;
+  return k;
+}
+
+__device__ __forceinline__ uint32_t bitrev(uint32_t x, int bits) { return bits ? __brev(x) >> (32 - bits) : 0; }
+
+// tw[j] = w^j for j < n/2 (w = primitive n-th root, or its inverse), Montgomery form;
+// tw[n/2] = n^{-1}.  `canon` != null also receives from_mont(tw[j]).
+__global__ void __launch_bounds__(256) fr_twiddle_kernel(const uint32_t* __restrict__ root28, const uint32_t* __restrict__ two_inv,
+                                                         int logn, uint32_t* __restrict__ tw, uint32_t* __restrict__ canon) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t half = logn ? (1u << (logn - 1)) : 0u;
+  if (j > half) return;
+  if (j == half) {
+    Fr ti = fp_load<FrParams>(two_inv), acc = Fr::one();
+    for (int k = 0; k < logn; k++) acc = acc * ti;
+    fp_store<FrParams>(tw + 8 * (size_t)half, acc);
+    return;
+  }
+  Fr w = fp_load<FrParams>(root28);
+  for (int k = logn; k < 28; k++) w = sqr(w);
+  Fr acc = Fr::one();
+  for (uint32_t e = j; e; e >>= 1) { if (e & 1u) acc = acc * w; w = sqr(w); }
+  fp_store<FrParams>(tw + 8 * (size_t)j, acc);
+  if (canon) fp_store<FrParams>(canon + 8 * (size_t)j, fp_from_mont<FrParams>(acc));
+}
+
+__global__ void __launch_bounds__(256) fr_bitrev_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int logn) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (1u << logn)) return;
+  fp_store<FrParams>(out + 8 * (size_t)bitrev(i, logn), fp_load<FrParams>(in + 8 * (size_t)i));
+}
+
+__global__ void __launch_bounds__(256) fr_butterfly_kernel(uint32_t* __restrict__ a, const uint32_t* __restrict__ tw, int logn, int s) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t half_n = 1u << (logn - 1);
+  if (t >= half_n) return;
+  uint32_t half = 1u << s;
+  uint32_t k = t & (half - 1), i = ((t >> s) << (s + 1)) + k, j = i + half;
+  Fr u = fp_load<FrParams>(a + 8 * (size_t)i);
+  Fr v = fp_load<FrParams>(a + 8 * (size_t)j) * fp_load<FrParams>(tw + 8 * (size_t)(k << (logn - 1 - s)));
+  fp_store<FrParams>(a + 8 * (size_t)i, u + v);
+  fp_store<FrParams>(a + 8 * (size_t)j, u - v);
+}
+
+__global__ void __launch_bounds__(256) fr_scale_kernel(uint32_t* __restrict__ a, const uint32_t* __restrict__ k, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fp_store<FrParams>(a + 8 * (size_t)i, fp_load<FrParams>(a + 8 * (size_t)i) * fp_load<FrParams>(k));
+}
+
+struct Twiddles {
+  DevBuf<uint32_t> tw, canon;
+  Twiddles(kb_ctx* ctx, int logn, bool inverse, bool want_canon)
+      : tw(ctx, 8 * ((size_t)(logn ? 1ull << (logn - 1) : 0) + 1)), canon(ctx, want_canon ? 8 * ((size_t)(logn ? 1ull << (logn - 1) : 0) + 1) : 0) {
+    DevBuf<uint32_t> c(ctx, 16);
+    KB_CUDA(cudaMemcpyAsync(c, inverse ? consts::FR_ROOT_2_28_INV : consts::FR_ROOT_2_28, 32, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(cudaMemcpyAsync(c.p + 8, consts::FR_TWO_INV, 32, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t half = logn ? (1u << (logn - 1)) : 0u;
+    KB_LAUNCH(ctx, fr_twiddle_kernel, cdiv(half + 1, 256), 256, 0, c.p, c.p + 8, logn, tw.p, want_canon ? canon.p : nullptr);
+  }
+};
+
+// in-place on d_data (natural order in and out); scale = apply 1/n after an inverse transform
+static void fr_ntt_dev(kb_ctx* ctx, uint32_t* d_data, int logn, bool inverse, bool scale) {
+  uint64_t n = 1ull << logn;
+  if (logn == 0) return;
+  Twiddles tw(ctx, logn, inverse, false);
+  DevBuf<uint32_t> tmp(ctx, 8 * n);
+  KB_LAUNCH(ctx, fr_bitrev_kernel, cdiv(n, 256), 256, 0, d_data, tmp.p, logn);
+  for (int s = 0; s < logn; s++) KB_LAUNCH(ctx, fr_butterfly_kernel, cdiv(n / 2, 256), 256, 0, tmp.p, tw.tw.p, logn, s);
+  KB_CUDA(cudaMemcpyAsync(d_data, tmp.p, 32 * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (inverse && scale) KB_LAUNCH(ctx, fr_scale_kernel, cdiv(n, 256), 256, 0, d_data, tw.tw.p + 8 * (n / 2), (uint32_t)n);
+}
+
+void fr_ntt(kb_ctx* ctx, uint32_t* d_data, uint64_t n, bool inverse) {
+  int logn = log2_exact(n);
+  if (logn < 0 || logn > 28) throw ApiError(KB_ERR_DOMAIN, "kb_fr_ntt: size must be a power of two <= 2^28");
+  fr_ntt_dev(ctx, d_data, logn, inverse, true);
+}
+
+// ------------------------------------------------------------------------------------------
+// quotient (p(x) - p(z)) / (x - z): chunked Horner, q_{i-1} = sum_{j >= i} p_j z^(j-i)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) quot_chunk_eval_kernel(const uint32_t* __restrict__ p, uint64_t d, const uint32_t* __restrict__ z,
+                                                              uint32_t L, uint32_t T, uint32_t* __restrict__ S, uint32_t* __restrict__ ZL) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  uint64_t lo = (uint64_t)t * L, hi = lo + L < d ? lo + L : d;
+  Fr zz = fp_load<FrParams>(z), acc = Fr::zero(), zp = Fr::one();
+  for (uint64_t i = hi; i-- > lo;) { acc = acc * zz + fp_load<FrParams>(p + 8 * i); zp = zp * zz; }
+  fp_store<FrParams>(S + 8 * (size_t)t, acc);       // sum_{j in chunk} p_j z^(j - lo)
+  fp_store<FrParams>(ZL + 8 * (size_t)t, zp);       // z^(chunk length)
+}
+// H[t] = S[t] + z^len_t * H[t+1], H[T] = 0   (suffix Horner values at chunk starts)
+__global__ void quot_chain_kernel(const uint32_t* __restrict__ S, const uint32_t* __restrict__ ZL, uint32_t T, uint32_t* __restrict__ H) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Fr acc = Fr::zero();
+  fp_store<FrParams>(H + 8 * (size_t)T, acc);
+  for (uint32_t t = T; t-- > 0;) {
+    acc = fp_load<FrParams>(S + 8 * (size_t)t) + fp_load<FrParams>(ZL + 8 * (size_t)t) * acc;
+    fp_store<FrParams>(H + 8 * (size_t)t, acc);
+  }
+}
+__global__ void __launch_bounds__(128) quot_write_kernel(const uint32_t* __restrict__ p, uint64_t d, const uint32_t* __restrict__ z,
+                                                         uint32_t L, uint32_t T, const uint32_t* __restrict__ H, uint32_t* __restrict__ q) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  uint64_t lo = (uint64_t)t * L, hi = lo + L < d ? lo + L : d;
+  Fr zz = fp_load<FrParams>(z), acc = fp_load<FrParams>(H + 8 * (size_t)(t + 1));
+  for (uint64_t i = hi; i-- > lo;) {
+    acc = acc * zz + fp_load<FrParams>(p + 8 * i);
+    if (i >= 1) fp_store<FrParams>(q + 8 * (i - 1), acc);
+  }
+}
+
+void open_batch(kb_ctx* ctx, const uint32_t* d_coeffs, uint64_t d, const uint32_t* d_points, uint64_t m,
+                uint32_t* d_proofs, uint8_t* d_inf) {
+  if (d >= 1 && d - 1 > ctx->srs_n)
+    throw ApiError(KB_ERR_POLY_TOO_LARGE, "PolynomialTooLarge(" + std::to_string(d - 1) + ", " + std::to_string(ctx->srs_n) + ")");
+  if (d <= 1) {  // constant polynomial: quotient is zero, proof is the identity
+    if (m) { KB_CUDA(cudaMemsetAsync(d_proofs, 0, 64 * m, ctx->stream)); KB_CUDA(cudaMemsetAsync(d_inf, 1, m, ctx->stream)); }
+    return;
+  }
+  uint32_t L = 16;
+  while ((uint64_t)L * L < d) L <<= 1;
+  uint32_t T = cdiv(d, L);
+  DevBuf<uint32_t> S(ctx, 8 * (size_t)T), ZL(ctx, 8 * (size_t)T), H(ctx, 8 * ((size_t)T + 1)), q(ctx, 8 * (d - 1));
+  for (uint64_t j = 0; j < m; j++) {
+    const uint32_t* z = d_points + 8 * j;
+    KB_LAUNCH(ctx, quot_chunk_eval_kernel, cdiv(T, 128), 128, 0, d_coeffs, d, z, L, T, S.p, ZL.p);
+    KB_LAUNCH(ctx, quot_chain_kernel, 1, 32, 0, S.p, ZL.p, T, H.p);
+    KB_LAUNCH(ctx, quot_write_kernel, cdiv(T, 128), 128, 0, d_coeffs, d, z, L, T, H.p, q.p);
+    msm_g1(ctx, q.p, 0, d - 1, d_proofs + 16 * j, d_inf + j);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// G1 NTT (XYZZ points, 32 limbs each)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) g1_bitrev_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int logn) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (1u << logn)) return;
+  st_g1x(out + 32 * (size_t)bitrev(i, logn), ld_g1x(in + 32 * (size_t)i));
+}
+
+__global__ void __launch_bounds__(128) g1_butterfly_kernel(uint32_t* __restrict__ a, const uint32_t* __restrict__ tw_canon, int logn, int s) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t half_n = 1u << (logn - 1);
+  if (t >= half_n) return;
+  uint32_t half = 1u << s;
+  uint32_t k = t & (half - 1), i = ((t >> s) << (s + 1)) + k, j = i + half;
+  G1 u = ld_g1x(a + 32 * (size_t)i);
+  G1 v = ld_g1x(a + 32 * (size_t)j);
+  if (k != 0 && !v.is_inf()) {
+    uint32_t kk[8];
+    const uint32_t* src = tw_canon + 8 * (size_t)(k << (logn - 1 - s));
+    for (int q = 0; q < 8; q++) kk[q] = src[q];
+    v = ec_mul(v, kk);
+  }
+  st_g1x(a + 32 * (size_t)i, ec_add(u, v));
+  st_g1x(a + 32 * (size_t)j, ec_add(u, neg(v)));
+}
+
+// in-place natural-order G1 transform on d_pts (XYZZ), unscaled
+static void g1_ntt_dev(kb_ctx* ctx, uint32_t* d_pts, int logn, bool inverse) {
+  if (logn == 0) return;
+  uint64_t n = 1ull << logn;
+  Twiddles tw(ctx, logn, inverse, true);
+  DevBuf<uint32_t> tmp(ctx, 32 * n);
+  KB_LAUNCH(ctx, g1_bitrev_kernel, cdiv(n, 256), 256, 0, d_pts, tmp.p, logn);
+  for (int s = 0; s < logn; s++) KB_LAUNCH(ctx, g1_butterfly_kernel, cdiv(n / 2, 128), 128, 0, tmp.p, tw.canon.p, logn, s);
+  KB_CUDA(cudaMemcpyAsync(d_pts, tmp.p, 128 * n, cudaMemcpyDeviceToDevice, ctx->stream));
+}
+
+// s[i] = srs[d-1-i] for i < d, infinity for d <= i < 2d   (src/kzg.rs:167-174)
+__global__ void __launch_bounds__(256) fk_build_s_kernel(const uint32_t* __restrict__ srs, uint32_t d, uint32_t* __restrict__ s) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * d) return;
+  G1 p = i < d ? to_xyzz(ld_g1(srs + 16 * (size_t)(d - 1 - i))) : G1::infinity();
+  st_g1x(s + 32 * (size_t)i, p);
+}
+// a = 0^d || p   (src/kzg.rs:178-179)
+__global__ void __launch_bounds__(256) fk_build_a_kernel(const uint32_t* __restrict__ p, uint32_t d, uint32_t* __restrict__ a) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * d) return;
+  Fr v = i < d ? Fr::zero() : fp_load<FrParams>(p + 8 * (size_t)(i - d));
+  fp_store<FrParams>(a + 8 * (size_t)i, v);
+}
+// hat_h[i] = (hat_a[i] * inv2d) * hat_s[i]   (src/kzg.rs:188-191)
+__global__ void __launch_bounds__(128) fk_pointwise_kernel(const uint32_t* __restrict__ hat_s, const uint32_t* __restrict__ hat_a,
+                                                           const uint32_t* __restrict__ inv2d, uint32_t n2, uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  Fr k = fp_from_mont<FrParams>(fp_load<FrParams>(hat_a + 8 * (size_t)i) * fp_load<FrParams>(inv2d));
+  st_g1x(out + 32 * (size_t)i, ec_mul(ld_g1x(hat_s + 32 * (size_t)i), k.v));
+}
+__global__ void __launch_bounds__(128) g1_xyzz_to_affine_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out_xy,
+                                                                uint8_t* __restrict__ out_inf) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1 p = ld_g1x(in + 32 * (size_t)i);
+  st_g1(out_xy + 16 * (size_t)i, to_affine(p));
+  out_inf[i] = p.is_inf() ? 1 : 0;
+}
+
+void fk_free(kb_ctx* ctx) {
+  for (auto& c : ctx->fk_cache) if (c.d_hat_s) cudaFree(c.d_hat_s);
+  ctx->fk_cache.clear();
+}
+
+void open_all_fk(kb_ctx* ctx, const uint32_t* d_coeffs, uint64_t d, uint32_t* d_proofs, uint8_t* d_inf) {
+  int logd = log2_exact(d);
+  if (logd < 0 || logd + 1 > 28) throw ApiError(KB_ERR_DOMAIN, "kb_open_all_fk: d must be a power of two with 2d <= 2^28");
+  if (d > ctx->srs_n) throw ApiError(KB_ERR_POLY_TOO_LARGE, "open_fk: d = " + std::to_string(d) + " exceeds SRS length " + std::to_string(ctx->srs_n));
+  const uint32_t n2 = (uint32_t)(2 * d);
+  // hat_s: cached per d
+  uint32_t* hat_s = nullptr;
+  for (auto& c : ctx->fk_cache) if (c.d == d) hat_s = c.d_hat_s;
+  if (!hat_s) {
+    KB_CUDA(cudaMalloc((void**)&hat_s, 128 * (size_t)n2));
+    KB_LAUNCH(ctx, fk_build_s_kernel, cdiv(n2, 256), 256, 0, ctx->d_srs, (uint32_t)d, hat_s);
+    g1_ntt_dev(ctx, hat_s, logd + 1, false);
+    kb_ctx::FkCache c; c.d = d; c.d_hat_s = hat_s;
+    ctx->fk_cache.push_back(c);
+  }
+  DevBuf<uint32_t> a(ctx, 8 * (size_t)n2), h(ctx, 32 * (size_t)n2);
+  KB_LAUNCH(ctx, fk_build_a_kernel, cdiv(n2, 256), 256, 0, d_coeffs, (uint32_t)d, a.p);
+  fr_ntt_dev(ctx, a.p, logd + 1, false, false);
+  Twiddles tw(ctx, logd + 1, true, false);  // only for (2d)^-1 at tw[d]
+  KB_LAUNCH(ctx, fk_pointwise_kernel, cdiv(n2, 128), 128, 0, hat_s, a.p, tw.tw.p + 8 * (size_t)d, n2, h.p);
+  g1_ntt_dev(ctx, h.p, logd + 1, true);
+  g1_ntt_dev(ctx, h.p, logd, false);  // first d entries (src/kzg.rs:197-200)
+  KB_LAUNCH(ctx, g1_xyzz_to_affine_kernel, cdiv(d, 128), 128, 0, h.p, (uint32_t)d, d_proofs, d_inf);
+}
+
+}  // namespace kb

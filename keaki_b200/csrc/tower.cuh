@@ -25,13 +25,13 @@ KB_HD Fq2 dbl(const Fq2& a) { Fq2 r; r.c0 = dbl(a.c0); r.c1 = dbl(a.c1); return 
 KB_HD Fq2 conj(const Fq2& a) { Fq2 r; r.c0 = a.c0; r.c1 = -a.c1; return r; }
 
 // Karatsuba: 3 base multiplications
-KB_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
+KB_FN Fq2 operator*(const Fq2& a, const Fq2& b) {
   Fq t0 = a.c0 * b.c0, t1 = a.c1 * b.c1;
   Fq s = (a.c0 + a.c1) * (b.c0 + b.c1);
   Fq2 r; r.c0 = t0 - t1; r.c1 = s - t0 - t1; return r;
 }
 // complex squaring: 2 base multiplications
-KB_HD Fq2 sqr(const Fq2& a) {
+KB_FN Fq2 sqr(const Fq2& a) {
   Fq t = a.c0 * a.c1;
   Fq2 r; r.c0 = (a.c0 + a.c1) * (a.c0 - a.c1); r.c1 = dbl(t); return r;
 }
@@ -42,7 +42,7 @@ KB_HD Fq2 mul_xi(const Fq2& a) {
   Fq t1 = dbl(dbl(dbl(a.c1))) + a.c1;  // 9 a1
   Fq2 r; r.c0 = t0 - a.c1; r.c1 = t1 + a.c0; return r;
 }
-KB_HD Fq2 inv(const Fq2& a) {
+KB_FN Fq2 inv(const Fq2& a) {
   Fq d = inv(sqr(a.c0) + sqr(a.c1));
   Fq2 r; r.c0 = a.c0 * d; r.c1 = -(a.c1 * d); return r;
 }

@@ -1,0 +1,290 @@
+// Batched witness encryption: `encapsulate` / `decapsulate` (src/kem.rs:13-72), the XOR layer of
+// `encrypt` / `decrypt` (src/enc.rs:19-55), `E::pairing` and `verify` (src/kzg.rs:127-151).
+// One thread per message / pairing (the batch dimension of src/vec.rs:63,75).
+//
+// Decapsulation is a full variable-base pairing per message.  Encapsulation is restructured
+// without changing any output bit (SURVEY.md §8d allows this):
+//   s_i  = e(r_i (C - v_i G1), G2) = A^{r_i} * gT^{-v_i r_i},  A = e(C, G2) (one pairing per
+//          commitment, cached), gT = e(G1, G2);  both are fixed-base GT exponentiations served from
+//          8-bit-window tables (32 windows x 255 entries), i.e. <= 64 Fq12 products per message;
+//   ct_i = r_i (tau_2 - a_i G2) = r_i tau_2 - (r_i a_i) G2: two fixed-base G2 multiplications from
+//          8-bit-window affine tables, i.e. <= 64 mixed additions per message.
+// GT bytes -> BLAKE3 XOF -> XOR with the message happen in the same kernel; GT never leaves chip.
+#include "ctx.cuh"
+#include "blake3.cuh"
+#include "consts_gen.cuh"
+
+namespace kb {
+
+__constant__ PairingConsts c_pc;
+
+void we_upload_consts() {
+  PairingConsts pc;
+  static_assert(sizeof(PairingConsts) == 20 * 64, "PairingConsts layout");
+  memcpy(&pc.frob, consts::FROB_GAMMA, sizeof(pc.frob));
+  memcpy(&pc.tw_x, consts::TW_X, 64);
+  memcpy(&pc.tw_y, consts::TW_Y, 64);
+  KB_CUDA(cudaMemcpyToSymbol(c_pc, &pc, sizeof(pc)));
+}
+
+static constexpr int WE_WIN = 32;          // 8-bit windows over 256 bits
+static constexpr int WE_ENT = 255;         // non-zero digits
+static constexpr size_t G2_TAB_LIMBS = (size_t)WE_WIN * WE_ENT * 32;
+static constexpr size_t GT_TAB_LIMBS = (size_t)WE_WIN * WE_ENT * 96;
+
+__device__ __forceinline__ G1Affine load_g1_flag(const uint32_t* xy, const uint8_t* inf, uint64_t i) {
+  if (inf && inf[i]) return G1Affine::infinity();
+  return ld_g1(xy + 16 * i);
+}
+__device__ __forceinline__ G2Affine load_g2_flag(const uint32_t* xy, const uint8_t* inf, uint64_t i) {
+  if (inf && inf[i]) return G2Affine::infinity();
+  return ld_g2(xy + 32 * i);
+}
+
+// ------------------------------------------------------------------------------------------
+// pairing / decrypt
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pairing_kernel(const uint32_t* __restrict__ g1, const uint8_t* __restrict__ g1_inf,
+                                                      const uint32_t* __restrict__ g2, const uint8_t* __restrict__ g2_inf,
+                                                      uint64_t n, uint32_t* __restrict__ gt_words) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = load_g1_flag(g1, g1_inf, i);
+  G2Affine q = load_g2_flag(g2, g2_inf, i);
+  Fq12 e = final_exponentiation(miller_loop(p, q, c_pc), c_pc);
+  uint32_t w[96];
+  gt_to_words(e, w);
+  for (int k = 0; k < 96; k++) gt_words[96 * i + k] = w[k];
+}
+
+__global__ void __launch_bounds__(128) decrypt_kernel(const uint32_t* __restrict__ proofs, const uint8_t* __restrict__ pinf,
+                                                      const uint32_t* __restrict__ ct, const uint8_t* __restrict__ cinf,
+                                                      const uint8_t* __restrict__ msg_ct, const uint64_t* __restrict__ off,
+                                                      uint64_t n, uint8_t* __restrict__ out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = load_g1_flag(proofs, pinf, i);
+  G2Affine q = load_g2_flag(ct, cinf, i);
+  Fq12 e = final_exponentiation(miller_loop(p, q, c_pc), c_pc);
+  uint32_t w[96];
+  gt_to_words(e, w);
+  uint64_t lo = off[i], hi = off[i + 1];
+  b3_gt_xof_xor(w, msg_ct + lo, out + lo, hi - lo);
+}
+
+// ------------------------------------------------------------------------------------------
+// fixed-base tables
+// ------------------------------------------------------------------------------------------
+// bases[w] = 2^(8w) * B (XYZZ), single thread (one-time per base point)
+__global__ void g2_window_bases_kernel(const uint32_t* __restrict__ base_xy, uint32_t* __restrict__ bases /* 32 * 64 limbs */) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  G2 acc = to_xyzz(ld_g2(base_xy));
+  for (int w = 0; w < WE_WIN; w++) {
+    st_fq2(bases + 64 * w, acc.x); st_fq2(bases + 64 * w + 16, acc.y);
+    st_fq2(bases + 64 * w + 32, acc.zz); st_fq2(bases + 64 * w + 48, acc.zzz);
+    if (w + 1 < WE_WIN) for (int k = 0; k < 8; k++) acc = ec_dbl(acc);
+  }
+}
+// tab[w][d-1] = d * bases[w], affine
+__global__ void __launch_bounds__(128) g2_table_fill_kernel(const uint32_t* __restrict__ bases, uint32_t* __restrict__ tab) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= WE_WIN * WE_ENT) return;
+  uint32_t w = t / WE_ENT, d = t % WE_ENT + 1;
+  G2 b;
+  b.x = ld_fq2(bases + 64 * w); b.y = ld_fq2(bases + 64 * w + 16); b.zz = ld_fq2(bases + 64 * w + 32); b.zzz = ld_fq2(bases + 64 * w + 48);
+  G2 acc = G2::infinity();
+  for (int bit = 7; bit >= 0; bit--) {
+    acc = ec_dbl(acc);
+    if ((d >> bit) & 1u) acc = ec_add(acc, b);
+  }
+  st_g2(tab + 32 * (size_t)t, to_affine(acc));
+}
+
+// bases[w] = A^(2^(8w)), single thread; A must be in GT (cyclotomic)
+__global__ void gt_window_bases_kernel(const uint32_t* __restrict__ a, uint32_t* __restrict__ bases /* 32 * 96 */) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Fq12 acc = ld_fq12(a);
+  for (int w = 0; w < WE_WIN; w++) {
+    st_fq12(bases + 96 * w, acc);
+    if (w + 1 < WE_WIN) for (int k = 0; k < 8; k++) acc = cyclotomic_sqr(acc);
+  }
+}
+// tab[w][d-1] = bases[w]^d
+__global__ void __launch_bounds__(128) gt_table_fill_kernel(const uint32_t* __restrict__ bases, uint32_t* __restrict__ tab) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= WE_WIN * WE_ENT) return;
+  uint32_t w = t / WE_ENT, d = t % WE_ENT + 1;
+  Fq12 b = ld_fq12(bases + 96 * w);
+  Fq12 acc = b;
+  int top = 31 - __clz(d);
+  for (int bit = top - 1; bit >= 0; bit--) {
+    acc = cyclotomic_sqr(acc);
+    if ((d >> bit) & 1u) acc = acc * b;
+  }
+  st_fq12(tab + 96 * (size_t)t, acc);
+}
+
+// single pairing e(P, G2gen) -> Montgomery Fq12 (for A = e(com, G2) and gT = e(G1, G2))
+__global__ void pairing_with_g2gen_kernel(const uint32_t* __restrict__ p_xy, uint32_t p_inf, const uint32_t* __restrict__ g2_gen,
+                                          uint32_t* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  G1Affine p = p_inf ? G1Affine::infinity() : ld_g1(p_xy);
+  G2Affine q = ld_g2(g2_gen);
+  st_fq12(out, final_exponentiation(miller_loop(p, q, c_pc), c_pc));
+}
+
+static void build_g2_table(kb_ctx* ctx, const uint32_t* d_base_xy, uint32_t* d_tab) {
+  DevBuf<uint32_t> bases(ctx, WE_WIN * 64);
+  KB_LAUNCH(ctx, g2_window_bases_kernel, 1, 32, 0, d_base_xy, bases);
+  KB_LAUNCH(ctx, g2_table_fill_kernel, cdiv(WE_WIN * WE_ENT, 128), 128, 0, bases, d_tab);
+}
+static void build_gt_table(kb_ctx* ctx, const uint32_t* d_a, uint32_t* d_tab) {
+  DevBuf<uint32_t> bases(ctx, WE_WIN * 96);
+  KB_LAUNCH(ctx, gt_window_bases_kernel, 1, 32, 0, d_a, bases);
+  KB_LAUNCH(ctx, gt_table_fill_kernel, cdiv(WE_WIN * WE_ENT, 128), 128, 0, bases, d_tab);
+}
+
+void we_init_tables(kb_ctx* ctx) {
+  KB_CUDA(cudaMalloc((void**)&ctx->d_g2_tab, G2_TAB_LIMBS * 4));
+  KB_CUDA(cudaMalloc((void**)&ctx->d_tau2_tab, G2_TAB_LIMBS * 4));
+  KB_CUDA(cudaMalloc((void**)&ctx->d_gt_tab, GT_TAB_LIMBS * 4));
+  KB_CUDA(cudaMalloc((void**)&ctx->d_com_tab, GT_TAB_LIMBS * 4));
+  DevBuf<uint32_t> g2(ctx, 32), g1(ctx, 16), gt(ctx, 96);
+  KB_CUDA(cudaMemcpyAsync(g2, consts::G2_GEN, 128, cudaMemcpyHostToDevice, ctx->stream));
+  KB_CUDA(cudaMemcpyAsync(g1, consts::G1_GEN, 64, cudaMemcpyHostToDevice, ctx->stream));
+  build_g2_table(ctx, g2, ctx->d_g2_tab);
+  KB_LAUNCH(ctx, pairing_with_g2gen_kernel, 1, 32, 0, g1, 0u, g2, gt);
+  build_gt_table(ctx, gt, ctx->d_gt_tab);
+  KB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+void we_set_tau2(kb_ctx* ctx, const uint32_t* d_tau2) { build_g2_table(ctx, d_tau2, ctx->d_tau2_tab); }
+
+void we_free(kb_ctx* ctx) {
+  cudaFree(ctx->d_g2_tab); cudaFree(ctx->d_tau2_tab); cudaFree(ctx->d_gt_tab); cudaFree(ctx->d_com_tab);
+  ctx->d_g2_tab = ctx->d_tau2_tab = ctx->d_gt_tab = ctx->d_com_tab = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+// encrypt
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t byte_of(const uint32_t* k, int w) { return (k[w >> 2] >> ((w & 3) * 8)) & 255u; }
+
+__global__ void __launch_bounds__(128) encrypt_kernel(const uint32_t* __restrict__ com_tab, const uint32_t* __restrict__ gt_tab,
+                                                      const uint32_t* __restrict__ tau2_tab, const uint32_t* __restrict__ g2_tab,
+                                                      const uint32_t* __restrict__ points, const uint32_t* __restrict__ values,
+                                                      const uint32_t* __restrict__ rs, const uint8_t* __restrict__ msgs,
+                                                      const uint64_t* __restrict__ off, uint64_t n,
+                                                      uint32_t* __restrict__ ct, uint8_t* __restrict__ ct_inf, uint8_t* __restrict__ msg_ct) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr r = fp_load<FrParams>(rs + 8 * i);
+  Fr v = fp_load<FrParams>(values + 8 * i);
+  Fr a = fp_load<FrParams>(points + 8 * i);
+  Fr kr = fp_from_mont<FrParams>(r);             // r
+  Fr ks = fp_from_mont<FrParams>(-(v * r));      // -v r
+  Fr ka = fp_from_mont<FrParams>(r * a);         // r alpha
+
+  // secret = A^r * gT^(-v r)
+  Fq12 s = Fq12::one();
+  bool started = false;
+  for (int w = 0; w < WE_WIN; w++) {
+    uint32_t d = byte_of(kr.v, w);
+    if (d) { Fq12 t = ld_fq12(com_tab + 96 * ((size_t)w * WE_ENT + d - 1)); s = started ? s * t : t; started = true; }
+    d = byte_of(ks.v, w);
+    if (d) { Fq12 t = ld_fq12(gt_tab + 96 * ((size_t)w * WE_ENT + d - 1)); s = started ? s * t : t; started = true; }
+  }
+  uint32_t words[96];
+  gt_to_words(s, words);
+  uint64_t lo = off[i], hi = off[i + 1];
+  b3_gt_xof_xor(words, msgs + lo, msg_ct + lo, hi - lo);
+
+  // ct = r tau_2 - (r alpha) G2
+  G2 acc = G2::infinity();
+  for (int w = 0; w < WE_WIN; w++) {
+    uint32_t d = byte_of(kr.v, w);
+    if (d) acc = ec_add_mixed(acc, ld_g2(tau2_tab + 32 * ((size_t)w * WE_ENT + d - 1)));
+    d = byte_of(ka.v, w);
+    if (d) { G2Affine t = ld_g2(g2_tab + 32 * ((size_t)w * WE_ENT + d - 1)); t.y = -t.y; acc = ec_add_mixed(acc, t); }
+  }
+  st_g2(ct + 32 * i, to_affine(acc));
+  ct_inf[i] = acc.is_inf() ? 1 : 0;
+}
+
+void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const uint32_t* d_points, const uint32_t* d_values,
+                   const uint32_t* d_r, const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n,
+                   uint32_t* d_ct, uint8_t* d_ct_inf, uint8_t* d_msg_ct) {
+  // (re)build the A = e(com, G2) table when the commitment changes
+  uint32_t key[17];
+  memcpy(key, h_com_xy, 64);
+  key[16] = com_inf ? 1u : 0u;
+  if (com_inf) memset(key, 0, 64);
+  if (!ctx->com_tab_valid || memcmp(key, ctx->com_cached, sizeof(key)) != 0) {
+    DevBuf<uint32_t> com(ctx, 16), g2(ctx, 32), a(ctx, 96);
+    KB_CUDA(cudaMemcpyAsync(com, key, 64, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(cudaMemcpyAsync(g2, consts::G2_GEN, 128, cudaMemcpyHostToDevice, ctx->stream));
+    KB_LAUNCH(ctx, pairing_with_g2gen_kernel, 1, 32, 0, com, key[16], g2, a);
+    build_gt_table(ctx, a, ctx->d_com_tab);
+    memcpy(ctx->com_cached, key, sizeof(key));
+    ctx->com_tab_valid = true;
+  }
+  if (!n) return;
+  timer_start(ctx, KB_T_ENCRYPT);
+  KB_LAUNCH(ctx, encrypt_kernel, cdiv(n, 128), 128, 0, ctx->d_com_tab, ctx->d_gt_tab, ctx->d_tau2_tab, ctx->d_g2_tab,
+            d_points, d_values, d_r, d_msgs, d_off, n, d_ct, d_ct_inf, d_msg_ct);
+  timer_stop(ctx, KB_T_ENCRYPT);
+}
+
+void pairing_batch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
+                   uint64_t n, uint8_t* d_gt_bytes) {
+  if (!n) return;
+  timer_start(ctx, KB_T_PAIRING);
+  KB_LAUNCH(ctx, pairing_kernel, cdiv(n, 128), 128, 0, d_g1, d_g1_inf, d_g2, d_g2_inf, n, reinterpret_cast<uint32_t*>(d_gt_bytes));
+  timer_stop(ctx, KB_T_PAIRING);
+}
+
+void decrypt_batch(kb_ctx* ctx, const uint32_t* d_proofs, const uint8_t* d_pinf, const uint32_t* d_ct, const uint8_t* d_cinf,
+                   const uint8_t* d_msg_ct, const uint64_t* d_off, uint64_t n, uint8_t* d_out) {
+  if (!n) return;
+  timer_start(ctx, KB_T_PAIRING);
+  KB_LAUNCH(ctx, decrypt_kernel, cdiv(n, 128), 128, 0, d_proofs, d_pinf, d_ct, d_cinf, d_msg_ct, d_off, n, d_out);
+  timer_stop(ctx, KB_T_PAIRING);
+}
+
+// ------------------------------------------------------------------------------------------
+// verify: e(C - v G1, G2) * e(-pi, tau_2 - a G2) == 1   (src/kzg.rs:127-151)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) verify_kernel(const uint32_t* __restrict__ com, const uint8_t* __restrict__ com_inf,
+                                                     const uint32_t* __restrict__ points, const uint32_t* __restrict__ values,
+                                                     const uint32_t* __restrict__ proofs, const uint8_t* __restrict__ pinf,
+                                                     const uint32_t* __restrict__ tau2_xy, const uint32_t* __restrict__ g2_gen,
+                                                     const uint32_t* __restrict__ g1_gen, uint64_t n, uint8_t* __restrict__ ok) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr kv = fp_from_mont<FrParams>(fp_load<FrParams>(values + 8 * i));
+  Fr ka = fp_from_mont<FrParams>(fp_load<FrParams>(points + 8 * i));
+  G1Affine c = load_g1_flag(com, com_inf, i);
+  G1Affine pi = load_g1_flag(proofs, pinf, i);
+  G2Affine g2 = ld_g2(g2_gen);
+  G1 vg = ec_mul(to_xyzz(ld_g1(g1_gen)), kv.v);
+  G1Affine lhs = to_affine(ec_add(to_xyzz(c), neg(vg)));
+  G2 ag = ec_mul(to_xyzz(g2), ka.v);
+  G2Affine rhs = to_affine(ec_add(to_xyzz(ld_g2(tau2_xy)), neg(ag)));
+  pi.y = -pi.y;
+  Fq12 f = miller_loop(lhs, g2, c_pc) * miller_loop(pi, rhs, c_pc);
+  Fq12 e = final_exponentiation(f, c_pc);
+  ok[i] = (e == Fq12::one()) ? 1 : 0;
+}
+
+void verify_batch(kb_ctx* ctx, const uint32_t* d_com, const uint8_t* d_com_inf, const uint32_t* d_points, const uint32_t* d_values,
+                  const uint32_t* d_proofs, const uint8_t* d_pinf, uint64_t n, uint8_t* d_ok) {
+  if (!n) return;
+  DevBuf<uint32_t> g2(ctx, 32), g1(ctx, 16);
+  KB_CUDA(cudaMemcpyAsync(g2, consts::G2_GEN, 128, cudaMemcpyHostToDevice, ctx->stream));
+  KB_CUDA(cudaMemcpyAsync(g1, consts::G1_GEN, 64, cudaMemcpyHostToDevice, ctx->stream));
+  // tau_2 itself is entry (w = 0, d = 1) of its fixed-base table
+  KB_LAUNCH(ctx, verify_kernel, cdiv(n, 128), 128, 0, d_com, d_com_inf, d_points, d_values, d_proofs, d_pinf,
+            ctx->d_tau2_tab, g2, g1, n, d_ok);
+}
+
+}  // namespace kb
