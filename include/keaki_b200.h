@@ -53,9 +53,11 @@ int32_t kb_srs_upload(kb_ctx* ctx, const uint32_t* g1_aff_xy /* n*16 */, uint64_
                       const uint32_t* tau_g2_xy /* 32 */);
 
 /* Synthetic SRS generated on the device from a known secret (harness + `KZGSetup::setup`,
- * src/kzg.rs:55-70): g1[i] = tau^i * G1 for i < n, tau_2 = tau * G2.  If out_g1_xy / out_tau_g2_xy
- * are non-null the points are also written there. */
-int32_t kb_srs_generate(kb_ctx* ctx, const uint32_t* tau /* 8, Montgomery Fr */, uint64_t n,
+ * src/kzg.rs:55-70): g1[i] = tau^(first_power + i) * G1 for i < n, tau_2 = tau * G2.  first_power = 0
+ * is the reference semantics; a rank holding the point range [k*n, (k+1)*n) of a larger SRS passes
+ * first_power = k*n.  If out_g1_xy / out_tau_g2_xy are non-null the points are
+ * also written there. */
+int32_t kb_srs_generate(kb_ctx* ctx, const uint32_t* tau /* 8, Montgomery Fr */, uint64_t first_power, uint64_t n,
                         uint32_t* out_g1_xy /* n*16 or NULL */, uint32_t* out_tau_g2_xy /* 32 or NULL */);
 
 uint64_t kb_srs_len(const kb_ctx* ctx);
@@ -66,6 +68,11 @@ uint64_t kb_srs_len(const kb_ctx* ctx);
  * Returns KB_ERR_POLY_TOO_LARGE if first + n > srs length. */
 int32_t kb_msm_g1(kb_ctx* ctx, const uint32_t* scalars /* n*8 */, uint64_t first, uint64_t n,
                   uint32_t out_xy[16], uint8_t* out_inf);
+
+/* out[i] = scalars[i] * G1 generator (batched fixed-base scalar multiplication: the `G1Affine::generator().mul(..)`
+ * of src/kzg.rs:57,135 and src/kem.rs:22; also the harness's trapdoor-proof generator). */
+int32_t kb_g1_mul_gen_batch(kb_ctx* ctx, const uint32_t* scalars /* n*8 */, uint64_t n,
+                            uint32_t* out_xy /* n*16 */, uint8_t* out_inf /* n */);
 
 /* Sum of n affine G1 points (combining per-GPU MSM partials after the gather). */
 int32_t kb_g1_sum(kb_ctx* ctx, const uint32_t* pts_xy /* n*16 */, const uint8_t* inf /* n or NULL */,

@@ -24,9 +24,10 @@ SIGNATURES = {
     "kb_ctx_destroy": (None, [_vp]),
     "kb_last_error": (ctypes.c_char_p, [_vp]),
     "kb_srs_upload": (_i32, [_vp, _vp, _u64, _vp]),
-    "kb_srs_generate": (_i32, [_vp, _vp, _u64, _vp, _vp]),
+    "kb_srs_generate": (_i32, [_vp, _vp, _u64, _u64, _vp, _vp]),
     "kb_srs_len": (_u64, [_vp]),
     "kb_msm_g1": (_i32, [_vp, _vp, _u64, _u64, _vp, _vp]),
+    "kb_g1_mul_gen_batch": (_i32, [_vp, _vp, _u64, _vp, _vp]),
     "kb_g1_sum": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),
     "kb_open_batch": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp]),
     "kb_open_all_fk": (_i32, [_vp, _vp, _u64, _vp, _vp]),
@@ -124,10 +125,10 @@ class Context:
         self._keep = (g1_xy, tau_g2_xy)
         self._check(self.lib.kb_srs_upload(self.h, _ptr(g1_xy), n, _ptr(tau_g2_xy)))
 
-    def srs_generate(self, tau_limbs, n, download=True):
+    def srs_generate(self, tau_limbs, n, download=True, first_power=0):
         g1 = np.zeros((n, 16), np.uint32) if download else None
         t2 = np.zeros(32, np.uint32)
-        self._check(self.lib.kb_srs_generate(self.h, _ptr(_u32(tau_limbs)), n, _ptr(g1), _ptr(t2)))
+        self._check(self.lib.kb_srs_generate(self.h, _ptr(_u32(tau_limbs)), first_power, n, _ptr(g1), _ptr(t2)))
         return g1, t2
 
     def srs_len(self):
@@ -140,6 +141,12 @@ class Context:
         out, inf = np.zeros(16, np.uint32), np.zeros(1, np.uint8)
         self._check(self.lib.kb_msm_g1(self.h, _ptr(scalars), first, n, _ptr(out), _ptr(inf)))
         return out, int(inf[0])
+
+    def g1_mul_gen_batch(self, scalars):
+        n = scalars.shape[0]
+        out, inf = np.zeros((n, 16), np.uint32), np.zeros(n, np.uint8)
+        self._check(self.lib.kb_g1_mul_gen_batch(self.h, _ptr(scalars), n, _ptr(out), _ptr(inf)))
+        return out, inf
 
     def g1_sum(self, pts_xy, inf=None):
         n = pts_xy.shape[0]

@@ -105,13 +105,13 @@ int32_t kb_srs_upload(kb_ctx* ctx, const uint32_t* g1_aff_xy, uint64_t n, const 
   KB_API_END(ctx)
 }
 
-int32_t kb_srs_generate(kb_ctx* ctx, const uint32_t* tau, uint64_t n, uint32_t* out_g1_xy, uint32_t* out_tau_g2_xy) {
+int32_t kb_srs_generate(kb_ctx* ctx, const uint32_t* tau, uint64_t first_power, uint64_t n, uint32_t* out_g1_xy, uint32_t* out_tau_g2_xy) {
   KB_API_BEGIN(ctx)
   need(tau != nullptr, "kb_srs_generate: null tau");
   fk_free(ctx);
   DevIn<uint32_t> dtau(ctx, tau, 8);
   DevBuf<uint32_t> tau2(ctx, 32);
-  srs_generate(ctx, dtau, n, tau2);
+  srs_generate(ctx, dtau, first_power, n, tau2);
   we_set_tau2(ctx, tau2);
   if (out_g1_xy && n) KB_CUDA(cudaMemcpyAsync(out_g1_xy, ctx->d_srs, n * 64, cudaMemcpyDefault, ctx->stream));
   if (out_tau_g2_xy) KB_CUDA(cudaMemcpyAsync(out_tau_g2_xy, tau2.p, 128, cudaMemcpyDefault, ctx->stream));
@@ -129,6 +129,17 @@ int32_t kb_msm_g1(kb_ctx* ctx, const uint32_t* scalars, uint64_t first, uint64_t
   DevBuf<uint8_t> inf_scratch(ctx, 1);
   DevOut<uint8_t> oi(ctx, out_inf, 1);
   msm_g1(ctx, s, first, n, o, out_inf ? oi.p : inf_scratch.p);
+  o.finish(); oi.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_g1_mul_gen_batch(kb_ctx* ctx, const uint32_t* scalars, uint64_t n, uint32_t* out_xy, uint8_t* out_inf) {
+  KB_API_BEGIN(ctx)
+  need(n == 0 || (scalars && out_xy && out_inf), "kb_g1_mul_gen_batch: null pointer");
+  DevIn<uint32_t> s(ctx, scalars, n * 8);
+  DevOut<uint32_t> o(ctx, out_xy, n * 16);
+  DevOut<uint8_t> oi(ctx, out_inf, n);
+  g1_mul_gen_batch(ctx, s, n, o, oi);
   o.finish(); oi.finish();
   KB_API_END(ctx)
 }

@@ -277,13 +277,13 @@ void msm_g1(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t first, uint64_t n, 
 // ------------------------------------------------------------------------------------------
 // Each thread owns a run of consecutive powers: tau^(t*RUN) by square-and-multiply, then RUN
 // scalar multiplications of the generator.
-__global__ void __launch_bounds__(128) srs_generate_kernel(const uint32_t* __restrict__ tau_m, uint64_t n, uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(128) srs_generate_kernel(const uint32_t* __restrict__ tau_m, uint64_t first_power, uint64_t n, uint32_t* __restrict__ out) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fr tau = fp_load<FrParams>(tau_m);
   // tau^i
   Fr acc = Fr::one(), base = tau;
-  for (uint64_t e = i; e; e >>= 1) { if (e & 1) acc = acc * base; base = sqr(base); }
+  for (uint64_t e = first_power + i; e; e >>= 1) { if (e & 1) acc = acc * base; base = sqr(base); }
   Fr k = fp_from_mont<FrParams>(acc);
   G1Affine g;
   g.x = Fq::one();
@@ -298,12 +298,28 @@ __global__ void srs_tau_g2_kernel(const uint32_t* __restrict__ tau_m, const uint
   st_g2(out, to_affine(ec_mul(to_xyzz(g), k.v)));
 }
 
-void srs_generate(kb_ctx* ctx, const uint32_t* d_tau, uint64_t n, uint32_t* d_tau_g2_out) {
+__global__ void __launch_bounds__(128) g1_mul_gen_kernel(const uint32_t* __restrict__ scalars, uint64_t n, uint32_t* __restrict__ out_xy,
+                                                         uint8_t* __restrict__ out_inf) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr k = fp_from_mont<FrParams>(fp_load<FrParams>(scalars + 8 * i));
+  G1Affine g;
+  g.x = Fq::one();
+  g.y = Fq::one() + Fq::one();
+  G1 r = ec_mul(to_xyzz(g), k.v);
+  st_g1(out_xy + 16 * i, to_affine(r));
+  out_inf[i] = r.is_inf() ? 1 : 0;
+}
+void g1_mul_gen_batch(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
+  if (n) KB_LAUNCH(ctx, g1_mul_gen_kernel, cdiv(n, 128), 128, 0, d_scalars, n, d_out_xy, d_out_inf);
+}
+
+void srs_generate(kb_ctx* ctx, const uint32_t* d_tau, uint64_t first_power, uint64_t n, uint32_t* d_tau_g2_out) {
   if (ctx->d_srs) { KB_CUDA(cudaFree(ctx->d_srs)); ctx->d_srs = nullptr; }
   msm_free_tables(ctx);
   KB_CUDA(cudaMalloc((void**)&ctx->d_srs, (size_t)(n ? n : 1) * 64));
   ctx->srs_n = n;
-  if (n) KB_LAUNCH(ctx, srs_generate_kernel, cdiv(n, 128), 128, 0, d_tau, n, ctx->d_srs);
+  if (n) KB_LAUNCH(ctx, srs_generate_kernel, cdiv(n, 128), 128, 0, d_tau, first_power, n, ctx->d_srs);
   DevBuf<uint32_t> gen(ctx, 32);
   KB_CUDA(cudaMemcpyAsync(gen, consts::G2_GEN, 128, cudaMemcpyHostToDevice, ctx->stream));
   KB_LAUNCH(ctx, srs_tau_g2_kernel, 1, 32, 0, d_tau, gen, d_tau_g2_out);

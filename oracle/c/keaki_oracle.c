@@ -1,0 +1,663 @@
+/* keaki_oracle.c — CPU restatement of the reference's hot path.  TEST INFRASTRUCTURE + CPU BASELINE,
+ * NOT PRODUCT CODE: only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline leg and
+ * --impl reference) may load the library built from this file.
+ *
+ * The reference (/root/reference) is pure Rust and delegates all arithmetic on this path to
+ * arkworks 0.4.x + blake3 1.5.4 (Cargo.lock:18-175), which are not vendored and cannot be built
+ * here (no cargo/rustc).  This file restates, in plain C with 4 x 64-bit-limb Montgomery
+ * arithmetic (the representation ark-ff uses), the ALGORITHMS those crates run for the keaki call
+ * sites, as published:
+ *   - ark-ec 0.4.2 VariableBaseMSM::msm_unchecked -> msm_bigint_wnaf: window c = ln(n)+2 (3 if n<32),
+ *     signed digits (make_digits), per-window buckets, running-sum reduction, Horner combine
+ *     [src/kzg.rs:98];
+ *   - SW Jacobian group law (add-2007-bl, madd-2007-bl, dbl-2009-l) and MSB-first double-and-add
+ *     scalar multiplication [src/kem.rs:22,30,36,37];
+ *   - BN optimal-ate Miller loop with homogeneous-projective line functions (G2Prepared) and the
+ *     Fuentes-Castaneda final exponentiation chain y0..y16 [src/kem.rs:30,58];
+ *   - ark-serialize uncompressed Fq12 bytes + BLAKE3 XOF [src/kem.rs:31-46,60-69];
+ *   - encapsulate / decapsulate / XOR exactly in the reference's operation order
+ *     [src/kem.rs:13-72, src/enc.rs:19-55], looped over messages like src/vec.rs:63,75.
+ * It is validated against the Python big-int oracle (oracle/bn254.py) in tests/test_oracle_c.py.
+ * PARITY: byte-level parity with arkworks itself is unpinned (no golden vectors exist upstream).
+ *
+ * Interface: field elements are 4 x u64 Montgomery limbs (R = 2^256), identical bytes to the
+ * product's C ABI.  Threads: OpenMP over messages / MSM windows (ark's `parallel` feature splits
+ * the same way); threads = 1 reproduces what the reference actually does (feature off).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef unsigned __int128 u128;
+typedef struct { uint64_t l[4]; } fe;
+typedef struct { uint64_t p[4]; uint64_t inv; fe one; fe r2; } field_t;
+
+static field_t FQ = {{0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull}, 0x87d20782e4866389ull,
+                     {{0xd35d438dc58f0d9dull, 0x0a78eb28f5c70b3dull, 0x666ea36f7879462cull, 0x0e0a77c19a07df2full}},
+                     {{0xf32cfc5b538afa89ull, 0xb5e71911d44501fbull, 0x47ab1eff0a417ff6ull, 0x06d89f71cab8351full}}};
+static field_t FR = {{0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull}, 0xc2e1f593efffffffull,
+                     {{0xac96341c4ffffffbull, 0x36fc76959f60cd29ull, 0x666ea36f7879462eull, 0x0e0a77c19a07df2full}},
+                     {{0x1bb8e645ae216da7ull, 0x53fe3ab1e35c59e3ull, 0x8c49833d53bb8085ull, 0x0216d0b17f4e44a5ull}}};
+
+/* ------------------------------------------------------------------ prime field */
+static int fe_is_zero(const fe* a) { return (a->l[0] | a->l[1] | a->l[2] | a->l[3]) == 0; }
+static int fe_eq(const fe* a, const fe* b) { return a->l[0] == b->l[0] && a->l[1] == b->l[1] && a->l[2] == b->l[2] && a->l[3] == b->l[3]; }
+static int geq_p(const uint64_t* a, const uint64_t* p) {
+  for (int i = 3; i >= 0; i--) { if (a[i] > p[i]) return 1; if (a[i] < p[i]) return 0; }
+  return 1;
+}
+static void sub_p(uint64_t* a, const uint64_t* p) {
+  u128 b = 0;
+  for (int i = 0; i < 4; i++) { u128 t = (u128)a[i] - p[i] - (uint64_t)b; a[i] = (uint64_t)t; b = (t >> 64) & 1; }
+}
+static void f_add(const field_t* F, fe* r, const fe* a, const fe* b) {
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) { c += (u128)a->l[i] + b->l[i]; r->l[i] = (uint64_t)c; c >>= 64; }
+  if (geq_p(r->l, F->p)) sub_p(r->l, F->p);
+}
+static void f_sub(const field_t* F, fe* r, const fe* a, const fe* b) {
+  u128 br = 0; uint64_t t[4];
+  for (int i = 0; i < 4; i++) { u128 d = (u128)a->l[i] - b->l[i] - (uint64_t)br; t[i] = (uint64_t)d; br = (d >> 64) & 1; }
+  if (br) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)t[i] + F->p[i]; t[i] = (uint64_t)c; c >>= 64; } }
+  memcpy(r->l, t, 32);
+}
+static void f_neg(const field_t* F, fe* r, const fe* a) { fe z = {{0, 0, 0, 0}}; f_sub(F, r, &z, a); }
+static void f_dbl(const field_t* F, fe* r, const fe* a) { f_add(F, r, a, a); }
+/* CIOS Montgomery product */
+static void f_mul(const field_t* F, fe* r, const fe* a, const fe* b) {
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) { c += (u128)a->l[j] * b->l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+    uint64_t m = t[0] * F->inv;
+    c = ((u128)m * F->p[0] + t[0]) >> 64;
+    for (int j = 1; j < 4; j++) { c += (u128)m * F->p[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  if (t[4] || geq_p(t, F->p)) sub_p(t, F->p);
+  memcpy(r->l, t, 32);
+}
+static void f_sqr(const field_t* F, fe* r, const fe* a) { f_mul(F, r, a, a); }
+static void f_from_mont(const field_t* F, fe* r, const fe* a) { fe o = {{1, 0, 0, 0}}; f_mul(F, r, a, &o); }
+static void f_pow(const field_t* F, fe* r, const fe* a, const uint64_t* e, int nlimbs) {
+  fe acc = F->one, base = *a;
+  for (int i = 0; i < nlimbs * 64; i++) {
+    if ((e[i >> 6] >> (i & 63)) & 1) f_mul(F, &acc, &acc, &base);
+    f_sqr(F, &base, &base);
+  }
+  *r = acc;
+}
+static void f_inv(const field_t* F, fe* r, const fe* a) {
+  uint64_t e[4]; memcpy(e, F->p, 32); e[0] -= 2;
+  f_pow(F, r, a, e, 4);
+}
+#define qadd(r, a, b) f_add(&FQ, r, a, b)
+#define qsub(r, a, b) f_sub(&FQ, r, a, b)
+#define qmul(r, a, b) f_mul(&FQ, r, a, b)
+#define qsqr(r, a) f_sqr(&FQ, r, a)
+#define qneg(r, a) f_neg(&FQ, r, a)
+#define qdbl(r, a) f_dbl(&FQ, r, a)
+
+/* ------------------------------------------------------------------ Fq2 = Fq[u]/(u^2+1) */
+typedef struct { fe c0, c1; } f2;
+static void f2_add(f2* r, const f2* a, const f2* b) { qadd(&r->c0, &a->c0, &b->c0); qadd(&r->c1, &a->c1, &b->c1); }
+static void f2_sub(f2* r, const f2* a, const f2* b) { qsub(&r->c0, &a->c0, &b->c0); qsub(&r->c1, &a->c1, &b->c1); }
+static void f2_neg(f2* r, const f2* a) { qneg(&r->c0, &a->c0); qneg(&r->c1, &a->c1); }
+static void f2_dbl(f2* r, const f2* a) { qdbl(&r->c0, &a->c0); qdbl(&r->c1, &a->c1); }
+static void f2_conj(f2* r, const f2* a) { r->c0 = a->c0; qneg(&r->c1, &a->c1); }
+static int f2_is_zero(const f2* a) { return fe_is_zero(&a->c0) && fe_is_zero(&a->c1); }
+static int f2_eq(const f2* a, const f2* b) { return fe_eq(&a->c0, &b->c0) && fe_eq(&a->c1, &b->c1); }
+static void f2_mul(f2* r, const f2* a, const f2* b) {
+  fe t0, t1, s0, s1, s;
+  qmul(&t0, &a->c0, &b->c0); qmul(&t1, &a->c1, &b->c1);
+  qadd(&s0, &a->c0, &a->c1); qadd(&s1, &b->c0, &b->c1); qmul(&s, &s0, &s1);
+  qsub(&r->c0, &t0, &t1); qsub(&s, &s, &t0); qsub(&r->c1, &s, &t1);
+}
+static void f2_sqr(f2* r, const f2* a) {
+  fe s, d, t;
+  qadd(&s, &a->c0, &a->c1); qsub(&d, &a->c0, &a->c1); qmul(&t, &a->c0, &a->c1);
+  qmul(&r->c0, &s, &d); qdbl(&r->c1, &t);
+}
+static void f2_mul_fq(f2* r, const f2* a, const fe* k) { qmul(&r->c0, &a->c0, k); qmul(&r->c1, &a->c1, k); }
+static void f2_mul_xi(f2* r, const f2* a) { /* (9 + u) a */
+  fe t0, t1, n0, n1;
+  qdbl(&t0, &a->c0); qdbl(&t0, &t0); qdbl(&t0, &t0); qadd(&t0, &t0, &a->c0);
+  qdbl(&t1, &a->c1); qdbl(&t1, &t1); qdbl(&t1, &t1); qadd(&t1, &t1, &a->c1);
+  qsub(&n0, &t0, &a->c1); qadd(&n1, &t1, &a->c0);
+  r->c0 = n0; r->c1 = n1;
+}
+static void f2_inv(f2* r, const f2* a) {
+  fe t0, t1, d;
+  qsqr(&t0, &a->c0); qsqr(&t1, &a->c1); qadd(&d, &t0, &t1); f_inv(&FQ, &d, &d);
+  qmul(&r->c0, &a->c0, &d); qmul(&t1, &a->c1, &d); qneg(&r->c1, &t1);
+}
+static f2 F2_ZERO, F2_ONE;
+
+/* ------------------------------------------------------------------ Fq6 = Fq2[v]/(v^3 - xi) */
+typedef struct { f2 c0, c1, c2; } f6;
+static void f6_add(f6* r, const f6* a, const f6* b) { f2_add(&r->c0, &a->c0, &b->c0); f2_add(&r->c1, &a->c1, &b->c1); f2_add(&r->c2, &a->c2, &b->c2); }
+static void f6_sub(f6* r, const f6* a, const f6* b) { f2_sub(&r->c0, &a->c0, &b->c0); f2_sub(&r->c1, &a->c1, &b->c1); f2_sub(&r->c2, &a->c2, &b->c2); }
+static void f6_neg(f6* r, const f6* a) { f2_neg(&r->c0, &a->c0); f2_neg(&r->c1, &a->c1); f2_neg(&r->c2, &a->c2); }
+static void f6_mul_v(f6* r, const f6* a) { f2 t; f2_mul_xi(&t, &a->c2); r->c2 = a->c1; r->c1 = a->c0; r->c0 = t; }
+static void f6_mul(f6* r, const f6* a, const f6* b) { /* Karatsuba (ark-ff Fp6 3-over-2) */
+  f2 v0, v1, v2, t0, t1, t2, x, y;
+  f2_mul(&v0, &a->c0, &b->c0); f2_mul(&v1, &a->c1, &b->c1); f2_mul(&v2, &a->c2, &b->c2);
+  f2_add(&x, &a->c1, &a->c2); f2_add(&y, &b->c1, &b->c2); f2_mul(&t0, &x, &y); f2_sub(&t0, &t0, &v1); f2_sub(&t0, &t0, &v2); f2_mul_xi(&t0, &t0); f2_add(&t0, &t0, &v0);
+  f2_add(&x, &a->c0, &a->c1); f2_add(&y, &b->c0, &b->c1); f2_mul(&t1, &x, &y); f2_sub(&t1, &t1, &v0); f2_sub(&t1, &t1, &v1); f2_mul_xi(&x, &v2); f2_add(&t1, &t1, &x);
+  f2_add(&x, &a->c0, &a->c2); f2_add(&y, &b->c0, &b->c2); f2_mul(&t2, &x, &y); f2_sub(&t2, &t2, &v0); f2_sub(&t2, &t2, &v2); f2_add(&t2, &t2, &v1);
+  r->c0 = t0; r->c1 = t1; r->c2 = t2;
+}
+static void f6_inv(f6* r, const f6* a) {
+  f2 t0, t1, t2, x, d;
+  f2_sqr(&t0, &a->c0); f2_mul(&x, &a->c1, &a->c2); f2_mul_xi(&x, &x); f2_sub(&t0, &t0, &x);
+  f2_sqr(&t1, &a->c2); f2_mul_xi(&t1, &t1); f2_mul(&x, &a->c0, &a->c1); f2_sub(&t1, &t1, &x);
+  f2_sqr(&t2, &a->c1); f2_mul(&x, &a->c0, &a->c2); f2_sub(&t2, &t2, &x);
+  f2 u, w; f2_mul(&u, &a->c2, &t1); f2_mul(&w, &a->c1, &t2); f2_add(&u, &u, &w); f2_mul_xi(&u, &u);
+  f2_mul(&d, &a->c0, &t0); f2_add(&d, &d, &u); f2_inv(&d, &d);
+  f2_mul(&r->c0, &t0, &d); f2_mul(&r->c1, &t1, &d); f2_mul(&r->c2, &t2, &d);
+}
+
+/* ------------------------------------------------------------------ Fq12 = Fq6[w]/(w^2 - v) */
+typedef struct { f6 c0, c1; } f12;
+static f12 F12_ONE;
+static void f12_mul(f12* r, const f12* a, const f12* b) {
+  f6 t0, t1, x, y, m;
+  f6_mul(&t0, &a->c0, &b->c0); f6_mul(&t1, &a->c1, &b->c1);
+  f6_add(&x, &a->c0, &a->c1); f6_add(&y, &b->c0, &b->c1); f6_mul(&m, &x, &y); f6_sub(&m, &m, &t0); f6_sub(&m, &m, &t1);
+  f6_mul_v(&x, &t1); f6_add(&r->c0, &t0, &x); r->c1 = m;
+}
+static void f12_sqr(f12* r, const f12* a) { f12_mul(r, a, a); }
+static void f12_conj(f12* r, const f12* a) { r->c0 = a->c0; f6_neg(&r->c1, &a->c1); }
+static void f12_inv(f12* r, const f12* a) {
+  f6 t0, t1, d;
+  f6_mul(&t0, &a->c0, &a->c0); f6_mul(&t1, &a->c1, &a->c1); f6_mul_v(&t1, &t1); f6_sub(&d, &t0, &t1); f6_inv(&d, &d);
+  f6_mul(&r->c0, &a->c0, &d); f6_mul(&t1, &a->c1, &d); f6_neg(&r->c1, &t1);
+}
+static int f12_eq(const f12* a, const f12* b) { return memcmp(a, b, sizeof(f12)) == 0; }
+/* coefficient of w^i (v = w^2) */
+static f2* f12_w(f12* a, int i) { f6* h = (i & 1) ? &a->c1 : &a->c0; return (i >> 1) == 0 ? &h->c0 : ((i >> 1) == 1 ? &h->c1 : &h->c2); }
+static f2 FROB[3][6], TW_X, TW_Y; /* xi^(i(q^k-1)/6), xi^((q-1)/3), xi^((q-1)/2) */
+static void f12_frob(f12* r, const f12* a, int k) {
+  f12 in = *a;
+  for (int i = 0; i < 6; i++) { f2 x = *f12_w(&in, i); if (k & 1) f2_conj(&x, &x); f2_mul(f12_w(r, i), &x, &FROB[k - 1][i]); }
+}
+/* mul_by_034: f * (c0 + d0 w + d1 w^3)  — ark-ff Fp12::mul_by_034, computed densely via the sparse operand */
+static void f12_mul_by_034(f12* f, const f2* c0, const f2* d0, const f2* d1) {
+  f12 l; memset(&l, 0, sizeof(l));
+  l.c0.c0 = *c0; l.c1.c0 = *d0; l.c1.c1 = *d1;
+  f12_mul(f, f, &l);
+}
+/* Granger-Scott cyclotomic squaring (ark-ff Fp12::cyclotomic_square) */
+static void fp4_square(f2* c0, f2* c1, const f2* a0, const f2* a1) {
+  f2 t0, t1, s;
+  f2_sqr(&t0, a0); f2_sqr(&t1, a1); f2_mul_xi(c0, &t1); f2_add(c0, c0, &t0);
+  f2_add(&s, a0, a1); f2_sqr(&s, &s); f2_sub(&s, &s, &t0); f2_sub(c1, &s, &t1);
+}
+static void f12_cyclo_sqr(f12* r, const f12* a) {
+  f2 r0 = a->c0.c0, r4 = a->c0.c1, r3 = a->c0.c2, r2 = a->c1.c0, r1 = a->c1.c1, r5 = a->c1.c2;
+  f2 t0, t1, t2, t3, t4, t5, x;
+  fp4_square(&t0, &t1, &r0, &r1);
+  fp4_square(&t2, &t3, &r2, &r3);
+  fp4_square(&t4, &t5, &r4, &r5);
+  f2 z0, z1, z2, z3, z4, z5;
+  f2_sub(&x, &t0, &r0); f2_dbl(&x, &x); f2_add(&z0, &x, &t0);      /* z0 = 3 t0 - 2 r0 */
+  f2_add(&x, &t1, &r1); f2_dbl(&x, &x); f2_add(&z1, &x, &t1);      /* z1 = 3 t1 + 2 r1 */
+  f2 t5x; f2_mul_xi(&t5x, &t5);
+  f2_add(&x, &t5x, &r2); f2_dbl(&x, &x); f2_add(&z2, &x, &t5x);    /* z2 = 3 xi t5 + 2 r2 */
+  f2_sub(&x, &t4, &r3); f2_dbl(&x, &x); f2_add(&z3, &x, &t4);      /* z3 = 3 t4 - 2 r3 */
+  f2_sub(&x, &t2, &r4); f2_dbl(&x, &x); f2_add(&z4, &x, &t2);      /* z4 = 3 t2 - 2 r4 */
+  f2_add(&x, &t3, &r5); f2_dbl(&x, &x); f2_add(&z5, &x, &t3);      /* z5 = 3 t3 + 2 r5 */
+  r->c0.c0 = z0; r->c0.c1 = z4; r->c0.c2 = z3; r->c1.c0 = z2; r->c1.c1 = z1; r->c1.c2 = z5;
+}
+
+/* ------------------------------------------------------------------ G1 (Jacobian, a = 0) */
+typedef struct { fe x, y; int inf; } g1a;
+typedef struct { fe x, y, z; } g1j; /* z = 0: identity */
+static int g1j_is_inf(const g1j* p) { return fe_is_zero(&p->z); }
+static void g1j_set_inf(g1j* p) { p->x = FQ.one; p->y = FQ.one; memset(&p->z, 0, 32); }
+static void g1j_dbl(g1j* r, const g1j* p) { /* dbl-2009-l */
+  if (g1j_is_inf(p)) { *r = *p; return; }
+  fe a, b, c, d, e, f, t;
+  qsqr(&a, &p->x); qsqr(&b, &p->y); qsqr(&c, &b);
+  qadd(&t, &p->x, &b); qsqr(&t, &t); qsub(&t, &t, &a); qsub(&t, &t, &c); qdbl(&d, &t);
+  qdbl(&e, &a); qadd(&e, &e, &a); qsqr(&f, &e);
+  fe z3; qmul(&z3, &p->y, &p->z); qdbl(&z3, &z3);
+  fe x3; qdbl(&t, &d); qsub(&x3, &f, &t);
+  fe c8; qdbl(&c8, &c); qdbl(&c8, &c8); qdbl(&c8, &c8);
+  qsub(&t, &d, &x3); qmul(&t, &e, &t); qsub(&r->y, &t, &c8);
+  r->x = x3; r->z = z3;
+}
+static void g1j_add_mixed(g1j* r, const g1j* p, const g1a* q) { /* madd-2007-bl */
+  if (q->inf) { *r = *p; return; }
+  if (g1j_is_inf(p)) { r->x = q->x; r->y = q->y; r->z = FQ.one; return; }
+  fe z1z1, u2, s2, h, hh, i, j, rr, v, t;
+  qsqr(&z1z1, &p->z); qmul(&u2, &q->x, &z1z1); qmul(&s2, &q->y, &p->z); qmul(&s2, &s2, &z1z1);
+  if (fe_eq(&u2, &p->x)) {
+    if (fe_eq(&s2, &p->y)) { g1j_dbl(r, p); return; }
+    g1j_set_inf(r); return;
+  }
+  qsub(&h, &u2, &p->x); qsqr(&hh, &h); qdbl(&i, &hh); qdbl(&i, &i); qmul(&j, &h, &i);
+  qsub(&rr, &s2, &p->y); qdbl(&rr, &rr); qmul(&v, &p->x, &i);
+  fe x3, y3, z3;
+  qsqr(&x3, &rr); qsub(&x3, &x3, &j); qdbl(&t, &v); qsub(&x3, &x3, &t);
+  qsub(&t, &v, &x3); qmul(&y3, &rr, &t); qmul(&t, &p->y, &j); qdbl(&t, &t); qsub(&y3, &y3, &t);
+  qadd(&z3, &p->z, &h); qsqr(&z3, &z3); qsub(&z3, &z3, &z1z1); qsub(&z3, &z3, &hh);
+  r->x = x3; r->y = y3; r->z = z3;
+}
+static void g1j_add(g1j* r, const g1j* p, const g1j* q) { /* add-2007-bl */
+  if (g1j_is_inf(p)) { *r = *q; return; }
+  if (g1j_is_inf(q)) { *r = *p; return; }
+  fe z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v, t;
+  qsqr(&z1z1, &p->z); qsqr(&z2z2, &q->z);
+  qmul(&u1, &p->x, &z2z2); qmul(&u2, &q->x, &z1z1);
+  qmul(&s1, &p->y, &q->z); qmul(&s1, &s1, &z2z2); qmul(&s2, &q->y, &p->z); qmul(&s2, &s2, &z1z1);
+  if (fe_eq(&u1, &u2)) {
+    if (fe_eq(&s1, &s2)) { g1j_dbl(r, p); return; }
+    g1j_set_inf(r); return;
+  }
+  qsub(&h, &u2, &u1); qdbl(&i, &h); qsqr(&i, &i); qmul(&j, &h, &i);
+  qsub(&rr, &s2, &s1); qdbl(&rr, &rr); qmul(&v, &u1, &i);
+  fe x3, y3, z3;
+  qsqr(&x3, &rr); qsub(&x3, &x3, &j); qdbl(&t, &v); qsub(&x3, &x3, &t);
+  qsub(&t, &v, &x3); qmul(&y3, &rr, &t); qmul(&t, &s1, &j); qdbl(&t, &t); qsub(&y3, &y3, &t);
+  qadd(&z3, &p->z, &q->z); qsqr(&z3, &z3); qsub(&z3, &z3, &z1z1); qsub(&z3, &z3, &z2z2); qmul(&z3, &z3, &h);
+  r->x = x3; r->y = y3; r->z = z3;
+}
+static void g1j_neg(g1j* r, const g1j* p) { r->x = p->x; r->z = p->z; qneg(&r->y, &p->y); }
+static void g1j_to_affine(g1a* r, const g1j* p) {
+  if (g1j_is_inf(p)) { memset(r, 0, sizeof(*r)); r->inf = 1; return; }
+  fe zi, zi2, zi3;
+  f_inv(&FQ, &zi, &p->z); qsqr(&zi2, &zi); qmul(&zi3, &zi2, &zi);
+  qmul(&r->x, &p->x, &zi2); qmul(&r->y, &p->y, &zi3); r->inf = 0;
+}
+/* MSB-first double-and-add over the canonical scalar (ark-ec `mul_bigint`) */
+static void g1j_mul(g1j* r, const g1j* p, const uint64_t k[4]) {
+  g1j acc; g1j_set_inf(&acc);
+  int started = 0;
+  for (int i = 255; i >= 0; i--) {
+    int bit = (k[i >> 6] >> (i & 63)) & 1;
+    if (started) g1j_dbl(&acc, &acc);
+    if (bit) { g1j_add(&acc, &acc, p); started = 1; }
+  }
+  *r = acc;
+}
+
+/* ------------------------------------------------------------------ G2 (Jacobian over Fq2) */
+typedef struct { f2 x, y; int inf; } g2a;
+typedef struct { f2 x, y, z; } g2j;
+static int g2j_is_inf(const g2j* p) { return f2_is_zero(&p->z); }
+static void g2j_set_inf(g2j* p) { p->x = F2_ONE; p->y = F2_ONE; p->z = F2_ZERO; }
+static void g2j_dbl(g2j* r, const g2j* p) {
+  if (g2j_is_inf(p)) { *r = *p; return; }
+  f2 a, b, c, d, e, f, t, z3, x3, c8;
+  f2_sqr(&a, &p->x); f2_sqr(&b, &p->y); f2_sqr(&c, &b);
+  f2_add(&t, &p->x, &b); f2_sqr(&t, &t); f2_sub(&t, &t, &a); f2_sub(&t, &t, &c); f2_dbl(&d, &t);
+  f2_dbl(&e, &a); f2_add(&e, &e, &a); f2_sqr(&f, &e);
+  f2_mul(&z3, &p->y, &p->z); f2_dbl(&z3, &z3);
+  f2_dbl(&t, &d); f2_sub(&x3, &f, &t);
+  f2_dbl(&c8, &c); f2_dbl(&c8, &c8); f2_dbl(&c8, &c8);
+  f2_sub(&t, &d, &x3); f2_mul(&t, &e, &t); f2_sub(&r->y, &t, &c8);
+  r->x = x3; r->z = z3;
+}
+static void g2j_add(g2j* r, const g2j* p, const g2j* q) {
+  if (g2j_is_inf(p)) { *r = *q; return; }
+  if (g2j_is_inf(q)) { *r = *p; return; }
+  f2 z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v, t, x3, y3, z3;
+  f2_sqr(&z1z1, &p->z); f2_sqr(&z2z2, &q->z);
+  f2_mul(&u1, &p->x, &z2z2); f2_mul(&u2, &q->x, &z1z1);
+  f2_mul(&s1, &p->y, &q->z); f2_mul(&s1, &s1, &z2z2); f2_mul(&s2, &q->y, &p->z); f2_mul(&s2, &s2, &z1z1);
+  if (f2_eq(&u1, &u2)) {
+    if (f2_eq(&s1, &s2)) { g2j_dbl(r, p); return; }
+    g2j_set_inf(r); return;
+  }
+  f2_sub(&h, &u2, &u1); f2_dbl(&i, &h); f2_sqr(&i, &i); f2_mul(&j, &h, &i);
+  f2_sub(&rr, &s2, &s1); f2_dbl(&rr, &rr); f2_mul(&v, &u1, &i);
+  f2_sqr(&x3, &rr); f2_sub(&x3, &x3, &j); f2_dbl(&t, &v); f2_sub(&x3, &x3, &t);
+  f2_sub(&t, &v, &x3); f2_mul(&y3, &rr, &t); f2_mul(&t, &s1, &j); f2_dbl(&t, &t); f2_sub(&y3, &y3, &t);
+  f2_add(&z3, &p->z, &q->z); f2_sqr(&z3, &z3); f2_sub(&z3, &z3, &z1z1); f2_sub(&z3, &z3, &z2z2); f2_mul(&z3, &z3, &h);
+  r->x = x3; r->y = y3; r->z = z3;
+}
+static void g2j_from_affine(g2j* r, const g2a* a) { if (a->inf) g2j_set_inf(r); else { r->x = a->x; r->y = a->y; r->z = F2_ONE; } }
+static void g2j_to_affine(g2a* r, const g2j* p) {
+  if (g2j_is_inf(p)) { memset(r, 0, sizeof(*r)); r->inf = 1; return; }
+  f2 zi, zi2, zi3;
+  f2_inv(&zi, &p->z); f2_sqr(&zi2, &zi); f2_mul(&zi3, &zi2, &zi);
+  f2_mul(&r->x, &p->x, &zi2); f2_mul(&r->y, &p->y, &zi3); r->inf = 0;
+}
+static void g2j_mul(g2j* r, const g2j* p, const uint64_t k[4]) {
+  g2j acc; g2j_set_inf(&acc);
+  int started = 0;
+  for (int i = 255; i >= 0; i--) {
+    int bit = (k[i >> 6] >> (i & 63)) & 1;
+    if (started) g2j_dbl(&acc, &acc);
+    if (bit) { g2j_add(&acc, &acc, p); started = 1; }
+  }
+  *r = acc;
+}
+
+/* ------------------------------------------------------------------ pairing (ark-ec models/bn) */
+static const int8_t ATE[65] = {0, 0, 0, 1, 0, 1, 0, -1, 0, 0, 1, -1, 0, 0, 1, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, -1, 0, 0, 0, 0,
+                               1, 1, 1, 0, 0, -1, 0, 0, 1, 0, 0, 0, 0, 0, -1, 0, 0, 1, 1, 0, 0, -1, 0, 0, 0, 1, 1, 0, -1, 0,
+                               0, 1, 0, 1, 1};
+static const uint64_t BN_Z = 0x44E992B44A6909F1ull;
+static f2 COEFF_B2;   /* 3 / (9 + u) */
+static fe TWO_INV;
+static g1a G1GEN; static g2a G2GEN;
+
+typedef struct { f2 x, y, z; } g2h; /* homogeneous projective */
+typedef struct { f2 c0, c1, c2; } ell_t;
+
+static void ell_double(g2h* r, ell_t* l) { /* G2HomProjective::double_in_place */
+  f2 a, b, c, e, f, g, h, i, j, e2, t;
+  f2_mul(&a, &r->x, &r->y); f2_mul_fq(&a, &a, &TWO_INV);
+  f2_sqr(&b, &r->y); f2_sqr(&c, &r->z);
+  f2_dbl(&t, &c); f2_add(&t, &t, &c); f2_mul(&e, &COEFF_B2, &t);
+  f2_dbl(&f, &e); f2_add(&f, &f, &e);
+  f2_add(&g, &b, &f); f2_mul_fq(&g, &g, &TWO_INV);
+  f2_add(&h, &r->y, &r->z); f2_sqr(&h, &h); f2_add(&t, &b, &c); f2_sub(&h, &h, &t);
+  f2_sub(&i, &e, &b);
+  f2_sqr(&j, &r->x);
+  f2_sqr(&e2, &e);
+  f2_sub(&t, &b, &f); f2_mul(&r->x, &a, &t);
+  f2_dbl(&t, &e2); f2_add(&t, &t, &e2); f2_sqr(&g, &g); f2_sub(&r->y, &g, &t);
+  f2_mul(&r->z, &b, &h);
+  f2_neg(&l->c0, &h); f2_dbl(&t, &j); f2_add(&l->c1, &t, &j); l->c2 = i;   /* D-twist: (-h, 3j, i) */
+}
+static void ell_add(g2h* r, const f2* qx, const f2* qy, ell_t* l) { /* G2HomProjective::add_in_place */
+  f2 theta, lambda, c, d, e, f, g, h, j, t;
+  f2_mul(&t, qy, &r->z); f2_sub(&theta, &r->y, &t);
+  f2_mul(&t, qx, &r->z); f2_sub(&lambda, &r->x, &t);
+  f2_sqr(&c, &theta); f2_sqr(&d, &lambda); f2_mul(&e, &lambda, &d); f2_mul(&f, &r->z, &c); f2_mul(&g, &r->x, &d);
+  f2_dbl(&t, &g); f2_add(&h, &e, &f); f2_sub(&h, &h, &t);
+  f2 ey; f2_mul(&ey, &e, &r->y);
+  f2_mul(&r->x, &lambda, &h);
+  f2_sub(&t, &g, &h); f2_mul(&t, &theta, &t); f2_sub(&r->y, &t, &ey);
+  f2_mul(&r->z, &r->z, &e);
+  f2 a, b; f2_mul(&a, &theta, qx); f2_mul(&b, &lambda, qy); f2_sub(&j, &a, &b);
+  l->c0 = lambda; f2_neg(&l->c1, &theta); l->c2 = j;                       /* D-twist: (lambda, -theta, j) */
+}
+static void ell_apply(f12* f, const ell_t* l, const g1a* p) { /* Bn::ell, TwistType::D */
+  f2 c0, c1;
+  f2_mul_fq(&c0, &l->c0, &p->y); f2_mul_fq(&c1, &l->c1, &p->x);
+  f12_mul_by_034(f, &c0, &c1, &l->c2);
+}
+static void miller_loop(f12* out, const g1a* p, const g2a* q) {
+  f12 f = F12_ONE;
+  if (p->inf || q->inf) { *out = f; return; }
+  g2h r = {q->x, q->y, F2_ONE};
+  f2 nqy; f2_neg(&nqy, &q->y);
+  ell_t l;
+  for (int i = 64; i >= 1; i--) {
+    if (i != 64) f12_sqr(&f, &f);
+    ell_double(&r, &l); ell_apply(&f, &l, p);
+    int bit = ATE[i - 1];
+    if (bit == 1) { ell_add(&r, &q->x, &q->y, &l); ell_apply(&f, &l, p); }
+    else if (bit == -1) { ell_add(&r, &q->x, &nqy, &l); ell_apply(&f, &l, p); }
+  }
+  f2 q1x, q1y, q2x, q2y, t;
+  f2_conj(&t, &q->x); f2_mul(&q1x, &t, &TW_X); f2_conj(&t, &q->y); f2_mul(&q1y, &t, &TW_Y);
+  f2_conj(&t, &q1x); f2_mul(&q2x, &t, &TW_X); f2_conj(&t, &q1y); f2_mul(&q2y, &t, &TW_Y); f2_neg(&q2y, &q2y);
+  ell_add(&r, &q1x, &q1y, &l); ell_apply(&f, &l, p);
+  ell_add(&r, &q2x, &q2y, &l); ell_apply(&f, &l, p);
+  *out = f;
+}
+static void exp_by_neg_x(f12* r, const f12* a) {
+  f12 acc = *a, base = *a;
+  for (int i = 61; i >= 0; i--) { f12_cyclo_sqr(&acc, &acc); if ((BN_Z >> i) & 1) f12_mul(&acc, &acc, &base); }
+  f12_conj(r, &acc);
+}
+static void final_exp(f12* out, const f12* fin) {
+  f12 f = *fin, f1, f2v, r, y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, y12, y13, y14, y15;
+  f12_conj(&f1, &f); f12_inv(&f2v, &f); f12_mul(&r, &f1, &f2v); f2v = r;
+  f12_frob(&r, &r, 2); f12_mul(&r, &r, &f2v);
+  exp_by_neg_x(&y0, &r); f12_cyclo_sqr(&y1, &y0); f12_cyclo_sqr(&y2, &y1); f12_mul(&y3, &y2, &y1);
+  exp_by_neg_x(&y4, &y3); f12_cyclo_sqr(&y5, &y4); exp_by_neg_x(&y6, &y5);
+  f12_conj(&y3, &y3); f12_conj(&y6, &y6);
+  f12_mul(&y7, &y6, &y4); f12_mul(&y8, &y7, &y3); f12_mul(&y9, &y8, &y1); f12_mul(&y10, &y8, &y4); f12_mul(&y11, &y10, &r);
+  f12_frob(&y12, &y9, 1); f12_mul(&y13, &y12, &y11); f12_frob(&y8, &y8, 2); f12_mul(&y14, &y8, &y13);
+  f12_conj(&r, &r); f12_mul(&y15, &r, &y9); f12_frob(&y15, &y15, 3); f12_mul(out, &y15, &y14);
+}
+static void pairing(f12* out, const g1a* p, const g2a* q) { f12 f; miller_loop(&f, p, q); final_exp(out, &f); }
+static void gt_serialize(uint8_t out[384], const f12* a) {
+  const f2* c[6] = {&a->c0.c0, &a->c0.c1, &a->c0.c2, &a->c1.c0, &a->c1.c1, &a->c1.c2};
+  for (int i = 0; i < 6; i++) { fe t; f_from_mont(&FQ, &t, &c[i]->c0); memcpy(out + 64 * i, t.l, 32); f_from_mont(&FQ, &t, &c[i]->c1); memcpy(out + 64 * i + 32, t.l, 32); }
+}
+
+/* ------------------------------------------------------------------ BLAKE3 (single chunk <= 1024 B, XOF) */
+static const uint32_t B3_IV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+static const uint8_t B3_PERM[16] = {2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8};
+static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+static void b3_g(uint32_t* s, int a, int b, int c, int d, uint32_t mx, uint32_t my) {
+  s[a] += s[b] + mx; s[d] = rotr(s[d] ^ s[a], 16); s[c] += s[d]; s[b] = rotr(s[b] ^ s[c], 12);
+  s[a] += s[b] + my; s[d] = rotr(s[d] ^ s[a], 8); s[c] += s[d]; s[b] = rotr(s[b] ^ s[c], 7);
+}
+static void b3_compress(const uint32_t cv[8], const uint32_t block[16], uint64_t counter, uint32_t blen, uint32_t flags, uint32_t out[16]) {
+  uint32_t s[16], m[16], t[16];
+  memcpy(s, cv, 32); memcpy(s + 8, B3_IV, 16);
+  s[12] = (uint32_t)counter; s[13] = (uint32_t)(counter >> 32); s[14] = blen; s[15] = flags;
+  memcpy(m, block, 64);
+  for (int r = 0; r < 7; r++) {
+    b3_g(s, 0, 4, 8, 12, m[0], m[1]); b3_g(s, 1, 5, 9, 13, m[2], m[3]); b3_g(s, 2, 6, 10, 14, m[4], m[5]); b3_g(s, 3, 7, 11, 15, m[6], m[7]);
+    b3_g(s, 0, 5, 10, 15, m[8], m[9]); b3_g(s, 1, 6, 11, 12, m[10], m[11]); b3_g(s, 2, 7, 8, 13, m[12], m[13]); b3_g(s, 3, 4, 9, 14, m[14], m[15]);
+    for (int i = 0; i < 16; i++) t[i] = m[B3_PERM[i]];
+    memcpy(m, t, 64);
+  }
+  for (int i = 0; i < 8; i++) { out[i] = s[i] ^ s[i + 8]; out[i + 8] = s[i + 8] ^ cv[i]; }
+}
+/* hash `len` <= 1024 bytes, write out_len XOF bytes */
+static void blake3_xof(const uint8_t* in, size_t len, uint8_t* out, size_t out_len) {
+  uint32_t cv[8], o[16], block[16];
+  memcpy(cv, B3_IV, 32);
+  size_t nblocks = len == 0 ? 1 : (len + 63) / 64;
+  for (size_t b = 0; b + 1 < nblocks; b++) {
+    memcpy(block, in + 64 * b, 64);
+    b3_compress(cv, block, 0, 64, b == 0 ? 1u : 0u, o);
+    memcpy(cv, o, 32);
+  }
+  size_t last = nblocks - 1, llen = len - 64 * last;
+  memset(block, 0, 64); memcpy(block, in + 64 * last, llen);
+  uint32_t flags = (last == 0 ? 1u : 0u) | 2u | 8u;
+  for (size_t off = 0, ctr = 0; off < out_len; off += 64, ctr++) {
+    b3_compress(cv, block, ctr, (uint32_t)llen, flags, o);
+    size_t n = out_len - off < 64 ? out_len - off : 64;
+    memcpy(out + off, o, n);
+  }
+}
+
+/* ------------------------------------------------------------------ init */
+static int g_init = 0;
+static void f2_pow_big(f2* r, const f2* a, const uint64_t* e, int nlimbs) {
+  f2 acc = F2_ONE, base = *a;
+  for (int i = 0; i < nlimbs * 64; i++) { if ((e[i >> 6] >> (i & 63)) & 1) f2_mul(&acc, &acc, &base); f2_sqr(&base, &base); }
+  *r = acc;
+}
+/* big-int helpers for the Frobenius exponents: (q^k - 1) / 6 * i fits in 13 limbs */
+static void big_mul_small(uint64_t* a, int n, uint64_t m) { u128 c = 0; for (int i = 0; i < n; i++) { c += (u128)a[i] * m; a[i] = (uint64_t)c; c >>= 64; } }
+static void big_mul(uint64_t* r, const uint64_t* a, int na, const uint64_t* b, int nb) {
+  memset(r, 0, 8 * (na + nb));
+  for (int i = 0; i < na; i++) { u128 c = 0; for (int j = 0; j < nb; j++) { c += (u128)a[i] * b[j] + r[i + j]; r[i + j] = (uint64_t)c; c >>= 64; } r[i + nb] = (uint64_t)c; }
+}
+static void big_div_small(uint64_t* a, int n, uint64_t d) { u128 rem = 0; for (int i = n - 1; i >= 0; i--) { u128 cur = (rem << 64) | a[i]; a[i] = (uint64_t)(cur / d); rem = cur % d; } }
+static void to_mont_q(fe* r, uint64_t v) { fe t = {{v, 0, 0, 0}}; f_mul(&FQ, r, &t, &FQ.r2); }
+
+void ko_init(void) {
+  if (g_init) return;
+  memset(&F2_ZERO, 0, sizeof(F2_ZERO)); F2_ONE = F2_ZERO; F2_ONE.c0 = FQ.one;
+  memset(&F12_ONE, 0, sizeof(F12_ONE)); F12_ONE.c0.c0 = F2_ONE;
+  f2 xi; to_mont_q(&xi.c0, 9); to_mont_q(&xi.c1, 1);
+  /* q^k as big integers */
+  uint64_t qk[3][13]; memset(qk, 0, sizeof(qk));
+  memcpy(qk[0], FQ.p, 32);
+  uint64_t tmp[16];
+  big_mul(tmp, qk[0], 4, FQ.p, 4); memcpy(qk[1], tmp, 64);
+  big_mul(tmp, qk[1], 8, FQ.p, 4); memcpy(qk[2], tmp, 96);
+  for (int k = 0; k < 3; k++) {
+    uint64_t e[13]; memcpy(e, qk[k], sizeof(e)); e[0] -= 1; big_div_small(e, 13, 6);
+    for (int i = 0; i < 6; i++) { uint64_t ei[13]; memcpy(ei, e, sizeof(ei)); big_mul_small(ei, 13, (uint64_t)i); f2_pow_big(&FROB[k][i], &xi, ei, 13); }
+  }
+  { uint64_t e[4]; memcpy(e, FQ.p, 32); e[0] -= 1; big_div_small(e, 4, 3); f2_pow_big(&TW_X, &xi, e, 4); }
+  { uint64_t e[4]; memcpy(e, FQ.p, 32); e[0] -= 1; big_div_small(e, 4, 2); f2_pow_big(&TW_Y, &xi, e, 4); }
+  f2 xi_inv; f2_inv(&xi_inv, &xi); fe three; to_mont_q(&three, 3); f2_mul_fq(&COEFF_B2, &xi_inv, &three);
+  fe two; to_mont_q(&two, 2); f_inv(&FQ, &TWO_INV, &two);
+  to_mont_q(&G1GEN.x, 1); to_mont_q(&G1GEN.y, 2); G1GEN.inf = 0;
+  static const uint64_t g2c[4][4] = {
+      {0x46debd5cd992f6edull, 0x674322d4f75edaddull, 0x426a00665e5c4479ull, 0x1800deef121f1e76ull},
+      {0x97e485b7aef312c2ull, 0xf1aa493335a9e712ull, 0x7260bfb731fb5d25ull, 0x198e9393920d483aull},
+      {0x4ce6cc0166fa7daaull, 0xe3d1e7690c43d37bull, 0x4aab71808dcb408full, 0x12c85ea5db8c6debull},
+      {0x55acdadcd122975bull, 0xbc4b313370b38ef3ull, 0xec9e99ad690c3395ull, 0x090689d0585ff075ull}};
+  fe* dst[4] = {&G2GEN.x.c0, &G2GEN.x.c1, &G2GEN.y.c0, &G2GEN.y.c1};
+  for (int i = 0; i < 4; i++) { fe t; memcpy(t.l, g2c[i], 32); f_mul(&FQ, dst[i], &t, &FQ.r2); }
+  G2GEN.inf = 0;
+  g_init = 1;
+}
+
+/* ------------------------------------------------------------------ exported API */
+static void load_g1(g1a* p, const uint64_t* xy, const uint8_t* inf, size_t i) {
+  if (inf && inf[i]) { memset(p, 0, sizeof(*p)); p->inf = 1; return; }
+  memcpy(p->x.l, xy + 8 * i, 32); memcpy(p->y.l, xy + 8 * i + 4, 32); p->inf = 0;
+}
+static void load_g2(g2a* p, const uint64_t* xy, const uint8_t* inf, size_t i) {
+  if (inf && inf[i]) { memset(p, 0, sizeof(*p)); p->inf = 1; return; }
+  memcpy(&p->x, xy + 16 * i, 64); memcpy(&p->y, xy + 16 * i + 8, 64); p->inf = 0;
+}
+static void store_g1(uint64_t* xy, uint8_t* inf, size_t i, const g1a* p) {
+  if (p->inf) memset(xy + 8 * i, 0, 64); else { memcpy(xy + 8 * i, p->x.l, 32); memcpy(xy + 8 * i + 4, p->y.l, 32); }
+  if (inf) inf[i] = (uint8_t)p->inf;
+}
+static void store_g2(uint64_t* xy, uint8_t* inf, size_t i, const g2a* p) {
+  if (p->inf) memset(xy + 16 * i, 0, 128); else { memcpy(xy + 16 * i, &p->x, 64); memcpy(xy + 16 * i + 8, &p->y, 64); }
+  if (inf) inf[i] = (uint8_t)p->inf;
+}
+
+int ko_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* ark-ec 0.4.2 msm_bigint_wnaf */
+static int ark_log2_ceil(size_t x) { if (x <= 1) return 0; int k = 0; size_t v = x - 1; while (v) { k++; v >>= 1; } return k; }
+static void make_digits(const uint64_t a[4], int w, int num_bits, int64_t* digits, int count) {
+  uint64_t radix = 1ull << w, mask = radix - 1, carry = 0;
+  (void)num_bits;
+  for (int i = 0; i < count; i++) {
+    int bit_offset = i * w, u = bit_offset / 64, bi = bit_offset % 64;
+    uint64_t buf;
+    if (bi < 64 - w || u == 3) buf = a[u] >> bi; else buf = (a[u] >> bi) | (a[u + 1] << (64 - bi));
+    uint64_t coef = carry + (buf & mask);
+    carry = (coef + radix / 2) >> w;
+    digits[i] = (int64_t)coef - (int64_t)(carry << w);
+  }
+  digits[count - 1] += (int64_t)(carry << w);
+}
+void ko_msm_g1(const uint64_t* bases_xy, const uint64_t* scalars_mont, size_t n, uint64_t* out_xy, uint8_t* out_inf, int threads) {
+  ko_init();
+  g1j total; g1j_set_inf(&total);
+  if (n) {
+    int c = n < 32 ? 3 : (ark_log2_ceil(n) * 69 / 100) + 2;
+    int num_bits = 254, count = (num_bits + c - 1) / c;
+    int64_t* digits = (int64_t*)malloc(sizeof(int64_t) * n * count);
+    for (size_t i = 0; i < n; i++) { fe s, k; memcpy(s.l, scalars_mont + 4 * i, 32); f_from_mont(&FR, &k, &s); make_digits(k.l, c, num_bits, digits + i * count, count); }
+    g1j* wsum = (g1j*)malloc(sizeof(g1j) * count);
+    size_t nb = (size_t)1 << (c - 1);
+#pragma omp parallel for schedule(dynamic) num_threads(threads)
+    for (int w = 0; w < count; w++) {
+      g1j* buckets = (g1j*)malloc(sizeof(g1j) * nb);
+      for (size_t b = 0; b < nb; b++) g1j_set_inf(&buckets[b]);
+      for (size_t i = 0; i < n; i++) {
+        int64_t d = digits[i * count + w];
+        if (d == 0) continue;
+        g1a base; load_g1(&base, bases_xy, NULL, i);
+        if (d > 0) g1j_add_mixed(&buckets[d - 1], &buckets[d - 1], &base);
+        else { qneg(&base.y, &base.y); g1j_add_mixed(&buckets[-d - 1], &buckets[-d - 1], &base); }
+      }
+      g1j run, res; g1j_set_inf(&run); g1j_set_inf(&res);
+      for (size_t b = nb; b-- > 0;) { g1j_add(&run, &run, &buckets[b]); g1j_add(&res, &res, &run); }
+      wsum[w] = res;
+      free(buckets);
+    }
+    g1j acc; g1j_set_inf(&acc);
+    for (int w = count - 1; w >= 1; w--) { g1j_add(&acc, &acc, &wsum[w]); for (int k = 0; k < c; k++) g1j_dbl(&acc, &acc); }
+    g1j_add(&total, &wsum[0], &acc);
+    free(wsum); free(digits);
+  }
+  g1a r; g1j_to_affine(&r, &total); store_g1(out_xy, out_inf, 0, &r);
+}
+
+void ko_g1_mul(const uint64_t* p_xy, uint8_t p_inf, const uint64_t* k_mont, uint64_t* out_xy, uint8_t* out_inf) {
+  ko_init();
+  g1a p; load_g1(&p, p_xy, &p_inf, 0);
+  fe s, k; memcpy(s.l, k_mont, 32); f_from_mont(&FR, &k, &s);
+  g1j pj, r; if (p.inf) g1j_set_inf(&pj); else { pj.x = p.x; pj.y = p.y; pj.z = FQ.one; }
+  g1j_mul(&r, &pj, k.l);
+  g1a a; g1j_to_affine(&a, &r); store_g1(out_xy, out_inf, 0, &a);
+}
+
+void ko_pairing_batch(const uint64_t* g1_xy, const uint8_t* g1_inf, const uint64_t* g2_xy, const uint8_t* g2_inf, size_t n, uint8_t* gt_bytes, int threads) {
+  ko_init();
+#pragma omp parallel for schedule(dynamic) num_threads(threads)
+  for (size_t i = 0; i < n; i++) {
+    g1a p; g2a q; load_g1(&p, g1_xy, g1_inf, i); load_g2(&q, g2_xy, g2_inf, i);
+    f12 e; pairing(&e, &p, &q); gt_serialize(gt_bytes + 384 * i, &e);
+  }
+}
+
+/* encapsulate + XOR exactly as src/kem.rs:13-50 / src/enc.rs:19-40 order the work, for i in 0..n (src/vec.rs:63) */
+void ko_encrypt_batch(const uint64_t* com_xy, uint8_t com_inf, const uint64_t* tau_g2_xy, const uint64_t* points, const uint64_t* values,
+                      const uint64_t* r_mont, const uint8_t* msgs, const uint64_t* off, size_t n,
+                      uint64_t* ct_xy, uint8_t* ct_inf, uint8_t* msg_ct, int threads) {
+  ko_init();
+  g1a com; load_g1(&com, com_xy, &com_inf, 0);
+  g2a tau2; load_g2(&tau2, tau_g2_xy, NULL, 0);
+#pragma omp parallel for schedule(dynamic) num_threads(threads)
+  for (size_t i = 0; i < n; i++) {
+    fe t, kv, ka, kr;
+    memcpy(t.l, values + 4 * i, 32); f_from_mont(&FR, &kv, &t);
+    memcpy(t.l, points + 4 * i, 32); f_from_mont(&FR, &ka, &t);
+    memcpy(t.l, r_mont + 4 * i, 32); f_from_mont(&FR, &kr, &t);
+    /* com_beta = commitment - G1 * value */
+    g1j g = {G1GEN.x, G1GEN.y, FQ.one}, vg, cb, cj;
+    g1j_mul(&vg, &g, kv.l); g1j_neg(&vg, &vg);
+    if (com.inf) g1j_set_inf(&cj); else { cj.x = com.x; cj.y = com.y; cj.z = FQ.one; }
+    g1j_add(&cb, &cj, &vg);
+    /* secret = e(com_beta * r, G2) */
+    g1j cbr; g1j_mul(&cbr, &cb, kr.l);
+    g1a cba; g1j_to_affine(&cba, &cbr);
+    f12 s; pairing(&s, &cba, &G2GEN);
+    uint8_t sb[384]; gt_serialize(sb, &s);
+    /* ct = (tau_2 - G2 * point) * r */
+    g2j g2, ag, tj, ta, ct;
+    g2j_from_affine(&g2, &G2GEN); g2j_mul(&ag, &g2, ka.l); f2_neg(&ag.y, &ag.y);
+    g2j_from_affine(&tj, &tau2); g2j_add(&ta, &tj, &ag);
+    g2j_mul(&ct, &ta, kr.l);
+    g2a cta; g2j_to_affine(&cta, &ct); store_g2(ct_xy, ct_inf, i, &cta);
+    /* key = BLAKE3-XOF(secret bytes); msg_ct = key ^ msg */
+    size_t lo = off[i], len = off[i + 1] - off[i];
+    uint8_t* key = msg_ct + lo;
+    blake3_xof(sb, 384, key, len);
+    for (size_t j = 0; j < len; j++) key[j] ^= msgs[lo + j];
+  }
+}
+
+/* decapsulate + XOR (src/kem.rs:55-72, src/enc.rs:44-55) for i in 0..n (src/vec.rs:75) */
+void ko_decrypt_batch(const uint64_t* proofs_xy, const uint8_t* proofs_inf, const uint64_t* ct_xy, const uint8_t* ct_inf,
+                      const uint8_t* msg_ct, const uint64_t* off, size_t n, uint8_t* out, int threads) {
+  ko_init();
+#pragma omp parallel for schedule(dynamic) num_threads(threads)
+  for (size_t i = 0; i < n; i++) {
+    g1a p; g2a q; load_g1(&p, proofs_xy, proofs_inf, i); load_g2(&q, ct_xy, ct_inf, i);
+    f12 s; pairing(&s, &p, &q);
+    uint8_t sb[384]; gt_serialize(sb, &s);
+    size_t lo = off[i], len = off[i + 1] - off[i];
+    blake3_xof(sb, 384, out + lo, len);
+    for (size_t j = 0; j < len; j++) out[lo + j] ^= msg_ct[lo + j];
+  }
+}
+
+void ko_blake3_xof(const uint8_t* in, size_t len, uint8_t* out, size_t out_len) { blake3_xof(in, len, out, out_len); }
