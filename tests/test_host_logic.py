@@ -1,0 +1,79 @@
+"""Host-side logic of the keaki mirror (no GPU): types, domains, ptau container, error behaviour."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from keaki_b200 import kzg, ptau
+from keaki_b200.types import (FQ_MODULUS, FR_MODULUS, FrRng, G1, G2, Radix2EvaluationDomain, fr_array, fr_from_limbs,
+                              fr_list, fr_to_limbs, pack_g1, unpack_g1)
+from oracle import bn254 as bn
+from tests import limbs as L
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+rng = random.Random(7)
+
+
+def test_moduli_and_limb_conversions_match_oracle():
+    assert FQ_MODULUS == bn.Q and FR_MODULUS == bn.R
+    for x in [0, 1, bn.R - 1, rng.randrange(bn.R)]:
+        assert np.array_equal(fr_to_limbs(x), L.fr_m(x)) and fr_from_limbs(fr_to_limbs(x)) == x
+    xs = [rng.randrange(bn.R) for _ in range(17)]
+    assert fr_list(fr_array(xs)) == xs and fr_array([]).shape == (0, 8)
+
+
+def test_domain_matches_ark_poly_conventions():
+    for n in (1, 2, 3, 8, 9, 1000):
+        d, o = Radix2EvaluationDomain(n), bn.Radix2Domain(n)
+        assert d.size == o.size and d.group_gen == o.group_gen and d.elements() == o.elements()
+    assert Radix2EvaluationDomain((1 << 20) + 1).size == 1 << 21   # "2^20 bits + padding rounds up" 
+    with pytest.raises(ValueError):
+        Radix2EvaluationDomain((1 << 28) + 1)
+
+
+def test_rng_is_deterministic_and_in_range():
+    a, b = FrRng(5), FrRng(5)
+    xs = [a.fr() for _ in range(50)]
+    assert xs == [b.fr() for _ in range(50)] and all(0 <= x < FR_MODULUS for x in xs)
+    assert FrRng(6).fr() != xs[0]
+
+
+def test_points_equality_and_packing():
+    g = G1.generator()
+    assert g.to_affine_ints() == (1, 2) and G1.zero().inf and G1.zero() == G1(None)
+    assert G1(g.xy) == g and G1(g.xy) != G1.zero() and G2.zero().to_affine_ints() is None
+    xy, inf = pack_g1([g, G1.zero()])
+    assert inf.tolist() == [0, 1] and unpack_g1(xy, inf) == [g, G1.zero()]
+
+
+def test_ptau_reader_on_reference_fixture_sections(tmp_path):
+    g1, g2 = ptau.get_powers_from_file(os.path.join(GOLD, "ppot_0080_01_mini.ptau"))
+    assert g1.shape == (3, 16) and g2.shape == (2, 32)               # src/kzg/ptau.rs:476-514
+    # the file's limbs ARE Montgomery limbs: passing them through is the correct decoding
+    assert L.g1_from(g1[0]) == bn.G1_GEN and L.g2_from(g2[0]) == bn.G2_GEN
+    # writer -> reader round trip, and container errors (src/kzg/ptau.rs:360-376)
+    out = tmp_path / "w.ptau"
+    ptau.write_ptau(str(out), g1, g2, power=1)
+    a, b = ptau.get_powers_from_file(str(out))
+    assert np.array_equal(a, g1) and np.array_equal(b, g2)
+    bad = tmp_path / "bad.ptau"
+    bad.write_bytes(b"nope" + out.read_bytes()[4:])
+    with pytest.raises(ptau.SetupFileError):
+        ptau.get_powers_from_file(str(bad))
+    with pytest.raises(ptau.SetupFileError):
+        ptau.get_powers_from_file(str(tmp_path / "missing.ptau"))
+    trunc = tmp_path / "trunc.ptau"
+    trunc.write_bytes(out.read_bytes()[:-5])
+    with pytest.raises(ptau.SetupFileError):
+        ptau.get_powers_from_file(str(trunc))
+
+
+def test_commit_size_check_happens_before_any_gpu_work():
+    """KZGError::PolynomialTooLarge(p.len(), g1_pow.len()) — src/kzg.rs:93-95; trailing zeros are stripped
+    like DensePolynomial::from_coefficients_slice does."""
+    setup = kzg.KZGSetup(None, np.zeros((2, 16), np.uint32), G2.zero())
+    with pytest.raises(kzg.KZGError) as e:
+        kzg.commit(setup, [1, 3, 2, 4])
+    assert "PolynomialTooLarge(4, 2)" in str(e.value)
+    assert kzg._strip([1, 2, 0, 0]) == [1, 2] and kzg._strip([0, 0]) == []
