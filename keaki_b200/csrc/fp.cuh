@@ -119,7 +119,7 @@ KB_HD void row_mad_shift(uint32_t* acc, const uint32_t* x, uint32_t s) {
 #pragma unroll
   for (int k = 0; k < 6; k += 2) { acc[k] = madc_lo_cc(x[k], s, acc[k + 2]); acc[k + 1] = madc_hi_cc(x[k], s, acc[k + 3]); }
   acc[6] = madc_lo_cc(x[6], s, 0);
-  acc[7] = madc_hi(x[6], s, 0);
+  acc[7] = madc_hi_cc(x[6], s, 0);  // carry-out is always 0; the .cc form lets ptxas fuse the pair into IMAD.WIDE.X
 }
 // same rows with the modulus as the (immediate) multiplicand
 template <class P, int ODD>
