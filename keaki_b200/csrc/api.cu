@@ -62,6 +62,7 @@ int32_t kb_ctx_create(int32_t device, kb_ctx** out) {
     for (auto& e : ctx->ev) KB_CUDA(cudaEventCreate(&e));
     we_upload_consts();
     we_init_tables(ctx);
+    vm_init(ctx);
     KB_CUDA(cudaStreamSynchronize(ctx->stream));
   } catch (const std::exception& e) {
     fprintf(stderr, "kb_ctx_create: %s\n", e.what());
@@ -80,6 +81,7 @@ void kb_ctx_destroy(kb_ctx* ctx) {
   msm_free_tables(ctx);
   fk_free(ctx);
   we_free(ctx);
+  vm_free(ctx);
   if (ctx->d_srs) cudaFree(ctx->d_srs);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -46,6 +46,12 @@ struct kb_ctx {
   uint32_t com_cached[17] = {0};     // xy + inf flag of the commitment the table was built for
   bool com_tab_valid = false;
 
+  // pairing VM (pairing_vm.cu): program + constants resident on the device
+  uint64_t* d_vm_prog = nullptr;
+  uint32_t* d_vm_consts = nullptr;
+  int vm_slots = 0, vm_width = 1, vm_gslots = 0;
+  uint64_t vm_out = 0;               // the six output slots, one byte each
+
   // FK open-all cache: hat_s = DFT_2d(reversed SRS prefix) per d
   struct FkCache { uint64_t d = 0; uint32_t* d_hat_s = nullptr; };
   std::vector<FkCache> fk_cache;
@@ -164,6 +170,8 @@ void we_init_tables(kb_ctx* ctx);                       // G2 generator + gT tab
 void we_set_tau2(kb_ctx* ctx, const uint32_t* d_tau2);  // tau_2 table (SRS upload)
 void we_free(kb_ctx* ctx);
 void we_upload_consts();
+void vm_init(kb_ctx* ctx);                             // pairing VM program upload (ctx creation)
+void vm_free(kb_ctx* ctx);
 void pairing_batch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
                    uint64_t n, uint8_t* d_gt_bytes);
 void decrypt_batch(kb_ctx* ctx, const uint32_t* d_proofs, const uint8_t* d_pinf, const uint32_t* d_ct, const uint8_t* d_cinf,

@@ -1,0 +1,215 @@
+// Batched pairing / decapsulation kernels built on the pairing VM (pairing_vm.cuh).
+// `decapsulate` (src/kem.rs:55-72) + the XOR of `decrypt` (src/enc.rs:44-55) over the batch of
+// `vec_decrypt` (src/vec.rs:72-81), and raw `E::pairing` (src/kem.rs:30,58; src/kzg.rs:148).
+//
+// Two adjacent lanes per pairing, lane t owning coordinate c_t of every Fq2 slot.  The slot file
+// lives in shared memory as uint4 halves, [slot][half][thread], so a warp's access to one half is
+// 512 contiguous bytes (conflict free, LDS.128 / STS.128).  Spilled values go to a global scratch
+// laid out the same way ([gslot][half][thread]: coalesced, L2-resident).  GT never leaves the chip on the decrypt
+// path: canonical bytes -> BLAKE3 XOF -> XOR happen in the epilogue.
+#define KB_INLINE_ALL
+#include "ctx.cuh"
+#include "blake3.cuh"
+#include "pairing_vm.cuh"
+#include "pairing_prog_gen.cuh"
+#include <cstdlib>
+
+namespace kb {
+
+static constexpr int VM_BLOCK = 128;   // threads per block = 64 / W pairings (2 W lanes each)
+
+struct DevLane {
+  uint4* sm;        // shared slot file ([slot][half][thread]), already offset by threadIdx.x
+  uint4* gl;        // global scratch ([gslot][half][thread]), already offset by the global thread index
+  size_t gstride;   // 2 x pairings in the launch (padded)
+  uint32_t t;       // which Fq2 coordinate this lane owns
+  uint32_t h;       // which word of a bundle this lane executes
+  uint32_t mask;    // lanes executing the same word (shuffle mask)
+  uint32_t row;     // uint4 per (slot, half) row of the slot file = 2 x pairings per block
+
+  __device__ __forceinline__ static Fq unpack(const uint4& q0, const uint4& q1) {
+    Fq r;
+    r.v[0] = q0.x; r.v[1] = q0.y; r.v[2] = q0.z; r.v[3] = q0.w;
+    r.v[4] = q1.x; r.v[5] = q1.y; r.v[6] = q1.z; r.v[7] = q1.w;
+    return r;
+  }
+  __device__ __forceinline__ Fq ld(uint32_t s) const {
+    const uint4* p = sm + (size_t)s * 2 * row;
+    return unpack(p[0], p[row]);
+  }
+  __device__ __forceinline__ Fq ld_partner(uint32_t s) const {   // the other coordinate of the same slot
+    const uint4* p = sm + (size_t)s * 2 * row + (t ? -1 : 1);
+    return unpack(p[0], p[row]);
+  }
+  __device__ __forceinline__ void st(uint32_t s, const Fq& a) const {
+    uint4* p = sm + (size_t)s * 2 * row;
+    p[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    p[row] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+  }
+  __device__ __forceinline__ Fq ldc(const uint32_t* p) const {
+    const uint4* q = reinterpret_cast<const uint4*>(p + 8 * t);
+    return unpack(__ldg(q), __ldg(q + 1));
+  }
+  __device__ __forceinline__ Fq ldg(uint32_t g) const {
+    const uint4* p = gl + (size_t)g * 2 * gstride;
+    return unpack(p[0], p[gstride]);
+  }
+  __device__ __forceinline__ void stg(uint32_t g, const Fq& a) const {
+    uint4* p = gl + (size_t)g * 2 * gstride;
+    p[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    p[gstride] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+  }
+  __device__ __forceinline__ Fq xchg(const Fq& a) const {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(mask, a.v[i], 1);
+    return r;
+  }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+
+// mode 0: write the 96 canonical GT words; mode 1: key = BLAKE3-XOF(GT bytes), out = key XOR msg_ct.
+// W = bundle width: a warp serves 16 / W pairings, lane = h * (32 / W) + pairing_in_warp * 2 + t.
+template <int W>
+__global__ void __launch_bounds__(VM_BLOCK) pairing_vm_kernel(const uint64_t* __restrict__ prog, const uint32_t* __restrict__ consts,
+                                                              uint64_t out_slots, const uint32_t* __restrict__ g1,
+                                                              const uint8_t* __restrict__ g1_inf, const uint32_t* __restrict__ g2,
+                                                              const uint8_t* __restrict__ g2_inf, uint64_t n, uint4* __restrict__ scratch,
+                                                              uint64_t gstride, int mode, uint32_t* __restrict__ gt_words,
+                                                              const uint8_t* __restrict__ msg_ct, const uint64_t* __restrict__ off,
+                                                              uint8_t* __restrict__ out) {
+  extern __shared__ uint4 vm_smem[];
+  constexpr uint32_t HALF = 32 / W, PAIRS_PER_WARP = 16 / W, PAIRS_PER_BLOCK = (VM_BLOCK / 32) * PAIRS_PER_WARP;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  DevLane ln;
+  ln.h = lane / HALF;
+  ln.t = lane & 1u;
+  ln.mask = W == 1 ? 0xffffffffu : (ln.h ? 0xffff0000u : 0x0000ffffu);
+  const uint32_t pair_in_block = warp * PAIRS_PER_WARP + ((lane % HALF) >> 1);
+  const uint64_t pairing = blockIdx.x * (uint64_t)PAIRS_PER_BLOCK + pair_in_block;
+  const bool live = pairing < n;
+  const uint64_t i = live ? pairing : n - 1;   // padding lanes recompute the last pairing (shuffles need all lanes)
+  ln.sm = vm_smem + pair_in_block * 2 + ln.t;
+  ln.gl = scratch + pairing * 2 + ln.t;
+  ln.gstride = gstride;
+  ln.row = PAIRS_PER_BLOCK * 2;
+
+  // slot 0 = (xP, yP), slot 1 = Q.x, slot 2 = Q.y: lane t takes coordinate t of each
+  Fq pc = fp_load<FqParams>(g1 + 16 * i + 8 * ln.t);
+  Fq qx = fp_load<FqParams>(g2 + 32 * i + 8 * ln.t);
+  Fq qy = fp_load<FqParams>(g2 + 32 * i + 16 + 8 * ln.t);
+  uint32_t pz = pc.is_zero(), qz = qx.is_zero() && qy.is_zero();
+  pz &= __shfl_xor_sync(0xffffffffu, pz, 1);
+  qz &= __shfl_xor_sync(0xffffffffu, qz, 1);
+  const bool trivial = (g1_inf && g1_inf[i]) || (g2_inf && g2_inf[i]) || pz || qz;
+  if (ln.h == 0) {
+    ln.st(0, pc);
+    ln.st(1, qx);
+    ln.st(2, qy);
+  }
+  __syncwarp();
+
+  vm::run<W>(prog, ln, consts);
+  __syncwarp();
+
+  // canonical (non-Montgomery) limbs of this lane's six coordinates, in ark-serialize order
+  uint32_t mine[48];
+#pragma unroll 1
+  for (int k = 0; k < 6; k++) {
+    Fq c = ln.ld((uint32_t)(out_slots >> (8 * k)) & 255u);
+    if (trivial) c = (k == 0 && ln.t == 0) ? Fq::one() : Fq::zero();   // arkworks skips pairs with an infinity: GT = 1
+    Fq unit = Fq::zero(); unit.v[0] = 1;
+    c = vm::mul1(c, unit);   // Montgomery form -> canonical integer
+#pragma unroll
+    for (int j = 0; j < 8; j++) mine[8 * k + j] = c.v[j];
+  }
+  if (mode == 0) {
+    if (live && ln.h == 0) {
+      uint4* o = reinterpret_cast<uint4*>(gt_words + 96 * i + 8 * ln.t);
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        o[4 * k] = make_uint4(mine[8 * k], mine[8 * k + 1], mine[8 * k + 2], mine[8 * k + 3]);
+        o[4 * k + 1] = make_uint4(mine[8 * k + 4], mine[8 * k + 5], mine[8 * k + 6], mine[8 * k + 7]);
+      }
+    }
+  } else {
+    uint32_t w[96];
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        uint32_t other = __shfl_xor_sync(0xffffffffu, mine[8 * k + j], 1);
+        w[16 * k + j] = ln.t ? other : mine[8 * k + j];
+        w[16 * k + 8 + j] = ln.t ? mine[8 * k + j] : other;
+      }
+    if (live && ln.h == 0 && ln.t == 0) {
+      uint64_t lo = off[i], hi = off[i + 1];
+      b3_gt_xof_xor(w, msg_ct + lo, out + lo, hi - lo);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+// slot file of one block: slots x 2 halves x (pairings per block x 2 coordinates) x 16 B
+static int vm_smem_bytes(const kb_ctx* ctx) { return ctx->vm_slots * 2 * (VM_BLOCK / ctx->vm_width) * 16; }
+
+// Program choice: KB_PAIRING_PROG="slots,width" (defaults to the fastest measured variant)
+void vm_init(kb_ctx* ctx) {
+  using namespace vmprog;
+  int slots = 14, width = 1;
+  if (const char* e = getenv("KB_PAIRING_PROG")) sscanf(e, "%d,%d", &slots, &width);
+  const Program* pr = nullptr;
+  for (int k = 0; k < NUM_PROGRAMS; k++) if (PROGRAMS[k].slots == slots && PROGRAMS[k].width == width) pr = &PROGRAMS[k];
+  if (!pr) throw CudaError("KB_PAIRING_PROG names a program variant that was not generated");
+  ctx->vm_slots = pr->slots;
+  ctx->vm_width = pr->width;
+  ctx->vm_gslots = pr->gslots;
+  ctx->vm_out = 0;
+  for (int k = 0; k < 6; k++) ctx->vm_out |= (uint64_t)pr->out[k] << (8 * k);
+  const size_t bytes = (size_t)(pr->len + pr->width) * 8;   // one padding bundle after END (prefetch)
+  KB_CUDA(cudaMalloc((void**)&ctx->d_vm_prog, bytes));
+  KB_CUDA(cudaMemsetAsync(ctx->d_vm_prog, 0, bytes, ctx->stream));
+  KB_CUDA(cudaMemcpyAsync(ctx->d_vm_prog, pr->words, (size_t)pr->len * 8, cudaMemcpyHostToDevice, ctx->stream));
+  KB_CUDA(cudaMalloc((void**)&ctx->d_vm_consts, sizeof(CONSTS)));
+  KB_CUDA(cudaMemcpyAsync(ctx->d_vm_consts, CONSTS, sizeof(CONSTS), cudaMemcpyHostToDevice, ctx->stream));
+  const int smem = vm_smem_bytes(ctx);
+  if (width == 1) KB_CUDA(cudaFuncSetAttribute(pairing_vm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  else KB_CUDA(cudaFuncSetAttribute(pairing_vm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+}
+
+void vm_free(kb_ctx* ctx) {
+  cudaFree(ctx->d_vm_prog); cudaFree(ctx->d_vm_consts);
+  ctx->d_vm_prog = nullptr; ctx->d_vm_consts = nullptr;
+}
+
+static void vm_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
+                      uint64_t n, int mode, uint32_t* d_gt_words, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out) {
+  const int pairs_per_block = VM_BLOCK / (2 * ctx->vm_width);
+  const unsigned blocks = cdiv(n, pairs_per_block);
+  const uint64_t gstride = (uint64_t)blocks * pairs_per_block * 2;
+  DevBuf<uint4> scratch(ctx, (size_t)ctx->vm_gslots * 2 * gstride);
+  timer_start(ctx, KB_T_PAIRING);
+  if (ctx->vm_width == 1)
+    KB_LAUNCH(ctx, pairing_vm_kernel<1>, blocks, VM_BLOCK, vm_smem_bytes(ctx), ctx->d_vm_prog, ctx->d_vm_consts,
+              ctx->vm_out, d_g1, d_g1_inf, d_g2, d_g2_inf, n, scratch.p, gstride, mode, d_gt_words, d_msg_ct, d_off, d_out);
+  else
+    KB_LAUNCH(ctx, pairing_vm_kernel<2>, blocks, VM_BLOCK, vm_smem_bytes(ctx), ctx->d_vm_prog, ctx->d_vm_consts,
+              ctx->vm_out, d_g1, d_g1_inf, d_g2, d_g2_inf, n, scratch.p, gstride, mode, d_gt_words, d_msg_ct, d_off, d_out);
+  timer_stop(ctx, KB_T_PAIRING);
+}
+
+void pairing_batch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
+                   uint64_t n, uint8_t* d_gt_bytes) {
+  if (!n) return;
+  vm_launch(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, 0, reinterpret_cast<uint32_t*>(d_gt_bytes), nullptr, nullptr, nullptr);
+}
+
+void decrypt_batch(kb_ctx* ctx, const uint32_t* d_proofs, const uint8_t* d_pinf, const uint32_t* d_ct, const uint8_t* d_cinf,
+                   const uint8_t* d_msg_ct, const uint64_t* d_off, uint64_t n, uint8_t* d_out) {
+  if (!n) return;
+  vm_launch(ctx, d_proofs, d_pinf, d_ct, d_cinf, n, 1, nullptr, d_msg_ct, d_off, d_out);
+}
+
+}  // namespace kb

@@ -42,37 +42,6 @@ __device__ __forceinline__ G2Affine load_g2_flag(const uint32_t* xy, const uint8
 }
 
 // ------------------------------------------------------------------------------------------
-// pairing / decrypt
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) pairing_kernel(const uint32_t* __restrict__ g1, const uint8_t* __restrict__ g1_inf,
-                                                      const uint32_t* __restrict__ g2, const uint8_t* __restrict__ g2_inf,
-                                                      uint64_t n, uint32_t* __restrict__ gt_words) {
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  G1Affine p = load_g1_flag(g1, g1_inf, i);
-  G2Affine q = load_g2_flag(g2, g2_inf, i);
-  Fq12 e = final_exponentiation(miller_loop(p, q, c_pc), c_pc);
-  uint32_t w[96];
-  gt_to_words(e, w);
-  for (int k = 0; k < 96; k++) gt_words[96 * i + k] = w[k];
-}
-
-__global__ void __launch_bounds__(128) decrypt_kernel(const uint32_t* __restrict__ proofs, const uint8_t* __restrict__ pinf,
-                                                      const uint32_t* __restrict__ ct, const uint8_t* __restrict__ cinf,
-                                                      const uint8_t* __restrict__ msg_ct, const uint64_t* __restrict__ off,
-                                                      uint64_t n, uint8_t* __restrict__ out) {
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  G1Affine p = load_g1_flag(proofs, pinf, i);
-  G2Affine q = load_g2_flag(ct, cinf, i);
-  Fq12 e = final_exponentiation(miller_loop(p, q, c_pc), c_pc);
-  uint32_t w[96];
-  gt_to_words(e, w);
-  uint64_t lo = off[i], hi = off[i + 1];
-  b3_gt_xof_xor(w, msg_ct + lo, out + lo, hi - lo);
-}
-
-// ------------------------------------------------------------------------------------------
 // fixed-base tables
 // ------------------------------------------------------------------------------------------
 // bases[w] = 2^(8w) * B (XYZZ), single thread (one-time per base point)
@@ -233,22 +202,6 @@ void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const
   KB_LAUNCH(ctx, encrypt_kernel, cdiv(n, 128), 128, 0, ctx->d_com_tab, ctx->d_gt_tab, ctx->d_tau2_tab, ctx->d_g2_tab,
             d_points, d_values, d_r, d_msgs, d_off, n, d_ct, d_ct_inf, d_msg_ct);
   timer_stop(ctx, KB_T_ENCRYPT);
-}
-
-void pairing_batch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
-                   uint64_t n, uint8_t* d_gt_bytes) {
-  if (!n) return;
-  timer_start(ctx, KB_T_PAIRING);
-  KB_LAUNCH(ctx, pairing_kernel, cdiv(n, 128), 128, 0, d_g1, d_g1_inf, d_g2, d_g2_inf, n, reinterpret_cast<uint32_t*>(d_gt_bytes));
-  timer_stop(ctx, KB_T_PAIRING);
-}
-
-void decrypt_batch(kb_ctx* ctx, const uint32_t* d_proofs, const uint8_t* d_pinf, const uint32_t* d_ct, const uint8_t* d_cinf,
-                   const uint8_t* d_msg_ct, const uint64_t* d_off, uint64_t n, uint8_t* d_out) {
-  if (!n) return;
-  timer_start(ctx, KB_T_PAIRING);
-  KB_LAUNCH(ctx, decrypt_kernel, cdiv(n, 128), 128, 0, d_proofs, d_pinf, d_ct, d_cinf, d_msg_ct, d_off, n, d_out);
-  timer_stop(ctx, KB_T_PAIRING);
 }
 
 // ------------------------------------------------------------------------------------------

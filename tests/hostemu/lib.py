@@ -22,7 +22,7 @@ def _stale():
 def load():
     if _stale():
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", OUT, SRC])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", OUT, SRC])
     return ctypes.CDLL(OUT)
 
 
