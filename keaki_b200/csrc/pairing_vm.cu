@@ -5,8 +5,8 @@
 // Two adjacent lanes per pairing, lane t owning coordinate c_t of every Fq2 slot.  The slot file
 // lives in shared memory as uint4 halves, [slot][half][thread], so a warp's access to one half is
 // 512 contiguous bytes (conflict free, LDS.128 / STS.128).  Spilled values go to a global scratch
-// laid out the same way ([gslot][half][thread]: coalesced, L2-resident).  GT never leaves the chip on the decrypt
-// path: canonical bytes -> BLAKE3 XOF -> XOR happen in the epilogue.
+// laid out the same way ([gslot][half][thread]: coalesced, L2-resident).  GT never leaves the chip
+// on the decrypt path: canonical bytes -> BLAKE3 XOF -> XOR happen in the epilogue.
 #define KB_INLINE_ALL
 #include "ctx.cuh"
 #include "blake3.cuh"
@@ -16,16 +16,13 @@
 
 namespace kb {
 
-static constexpr int VM_BLOCK = 128;   // threads per block = 64 / W pairings (2 W lanes each)
+static constexpr int VM_BLOCK = 128;   // threads per block = 64 pairings (two lanes each)
 
 struct DevLane {
   uint4* sm;        // shared slot file ([slot][half][thread]), already offset by threadIdx.x
   uint4* gl;        // global scratch ([gslot][half][thread]), already offset by the global thread index
-  size_t gstride;   // 2 x pairings in the launch (padded)
+  size_t gstride;   // threads in the launch (2 x pairings, padded to the block)
   uint32_t t;       // which Fq2 coordinate this lane owns
-  uint32_t h;       // which word of a bundle this lane executes
-  uint32_t mask;    // lanes executing the same word (shuffle mask)
-  uint32_t row;     // uint4 per (slot, half) row of the slot file = 2 x pairings per block
 
   __device__ __forceinline__ static Fq unpack(const uint4& q0, const uint4& q1) {
     Fq r;
@@ -34,17 +31,17 @@ struct DevLane {
     return r;
   }
   __device__ __forceinline__ Fq ld(uint32_t s) const {
-    const uint4* p = sm + (size_t)s * 2 * row;
-    return unpack(p[0], p[row]);
+    const uint4* p = sm + (size_t)s * 2 * VM_BLOCK;
+    return unpack(p[0], p[VM_BLOCK]);
   }
   __device__ __forceinline__ Fq ld_partner(uint32_t s) const {   // the other coordinate of the same slot
-    const uint4* p = sm + (size_t)s * 2 * row + (t ? -1 : 1);
-    return unpack(p[0], p[row]);
+    const uint4* p = sm + (size_t)s * 2 * VM_BLOCK + (t ? -1 : 1);
+    return unpack(p[0], p[VM_BLOCK]);
   }
   __device__ __forceinline__ void st(uint32_t s, const Fq& a) const {
-    uint4* p = sm + (size_t)s * 2 * row;
+    uint4* p = sm + (size_t)s * 2 * VM_BLOCK;
     p[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
-    p[row] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+    p[VM_BLOCK] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
   }
   __device__ __forceinline__ Fq ldc(const uint32_t* p) const {
     const uint4* q = reinterpret_cast<const uint4*>(p + 8 * t);
@@ -62,37 +59,33 @@ struct DevLane {
   __device__ __forceinline__ Fq xchg(const Fq& a) const {
     Fq r;
 #pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(mask, a.v[i], 1);
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], 1);
     return r;
   }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 
 // mode 0: write the 96 canonical GT words; mode 1: key = BLAKE3-XOF(GT bytes), out = key XOR msg_ct.
-// W = bundle width: a warp serves 16 / W pairings, lane = h * (32 / W) + pairing_in_warp * 2 + t.
-template <int W>
-__global__ void __launch_bounds__(VM_BLOCK) pairing_vm_kernel(const uint64_t* __restrict__ prog, const uint32_t* __restrict__ consts,
-                                                              uint64_t out_slots, const uint32_t* __restrict__ g1,
-                                                              const uint8_t* __restrict__ g1_inf, const uint32_t* __restrict__ g2,
-                                                              const uint8_t* __restrict__ g2_inf, uint64_t n, uint4* __restrict__ scratch,
-                                                              uint64_t gstride, int mode, uint32_t* __restrict__ gt_words,
-                                                              const uint8_t* __restrict__ msg_ct, const uint64_t* __restrict__ off,
-                                                              uint8_t* __restrict__ out) {
+// A warp serves 16 pairings: lane = pairing_in_warp * 2 + t.  MINB = resident blocks per SM the register
+// allocation is held to (the slot budget decides how many fit in shared memory).
+template <int MINB>
+__global__ void __launch_bounds__(VM_BLOCK, MINB) pairing_vm_kernel(const uint64_t* __restrict__ prog, const uint32_t* __restrict__ consts,
+                                                                    uint64_t out_slots, const uint32_t* __restrict__ g1,
+                                                                    const uint8_t* __restrict__ g1_inf, const uint32_t* __restrict__ g2,
+                                                                    const uint8_t* __restrict__ g2_inf, uint64_t n, uint4* __restrict__ scratch,
+                                                                    uint64_t gstride, int mode, uint32_t* __restrict__ gt_words,
+                                                                    const uint8_t* __restrict__ msg_ct, const uint64_t* __restrict__ off,
+                                                                    uint8_t* __restrict__ out) {
   extern __shared__ uint4 vm_smem[];
-  constexpr uint32_t HALF = 32 / W, PAIRS_PER_WARP = 16 / W, PAIRS_PER_BLOCK = (VM_BLOCK / 32) * PAIRS_PER_WARP;
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  DevLane ln;
-  ln.h = lane / HALF;
-  ln.t = lane & 1u;
-  ln.mask = W == 1 ? 0xffffffffu : (ln.h ? 0xffff0000u : 0x0000ffffu);
-  const uint32_t pair_in_block = warp * PAIRS_PER_WARP + ((lane % HALF) >> 1);
-  const uint64_t pairing = blockIdx.x * (uint64_t)PAIRS_PER_BLOCK + pair_in_block;
+  const uint64_t gtid = blockIdx.x * (uint64_t)VM_BLOCK + threadIdx.x;
+  const uint64_t pairing = gtid >> 1;
   const bool live = pairing < n;
   const uint64_t i = live ? pairing : n - 1;   // padding lanes recompute the last pairing (shuffles need all lanes)
-  ln.sm = vm_smem + pair_in_block * 2 + ln.t;
-  ln.gl = scratch + pairing * 2 + ln.t;
+  DevLane ln;
+  ln.t = threadIdx.x & 1u;
+  ln.sm = vm_smem + threadIdx.x;
+  ln.gl = scratch + gtid;
   ln.gstride = gstride;
-  ln.row = PAIRS_PER_BLOCK * 2;
 
   // slot 0 = (xP, yP), slot 1 = Q.x, slot 2 = Q.y: lane t takes coordinate t of each
   Fq pc = fp_load<FqParams>(g1 + 16 * i + 8 * ln.t);
@@ -102,14 +95,11 @@ __global__ void __launch_bounds__(VM_BLOCK) pairing_vm_kernel(const uint64_t* __
   pz &= __shfl_xor_sync(0xffffffffu, pz, 1);
   qz &= __shfl_xor_sync(0xffffffffu, qz, 1);
   const bool trivial = (g1_inf && g1_inf[i]) || (g2_inf && g2_inf[i]) || pz || qz;
-  if (ln.h == 0) {
-    ln.st(0, pc);
-    ln.st(1, qx);
-    ln.st(2, qy);
-  }
-  __syncwarp();
+  ln.st(0, pc);
+  ln.st(1, qx);
+  ln.st(2, qy);
 
-  vm::run<W>(prog, ln, consts);
+  vm::run(prog, ln, consts);
   __syncwarp();
 
   // canonical (non-Montgomery) limbs of this lane's six coordinates, in ark-serialize order
@@ -124,7 +114,7 @@ __global__ void __launch_bounds__(VM_BLOCK) pairing_vm_kernel(const uint64_t* __
     for (int j = 0; j < 8; j++) mine[8 * k + j] = c.v[j];
   }
   if (mode == 0) {
-    if (live && ln.h == 0) {
+    if (live) {
       uint4* o = reinterpret_cast<uint4*>(gt_words + 96 * i + 8 * ln.t);
 #pragma unroll
       for (int k = 0; k < 6; k++) {
@@ -142,7 +132,7 @@ __global__ void __launch_bounds__(VM_BLOCK) pairing_vm_kernel(const uint64_t* __
         w[16 * k + j] = ln.t ? other : mine[8 * k + j];
         w[16 * k + 8 + j] = ln.t ? mine[8 * k + j] : other;
       }
-    if (live && ln.h == 0 && ln.t == 0) {
+    if (live && ln.t == 0) {
       uint64_t lo = off[i], hi = off[i + 1];
       b3_gt_xof_xor(w, msg_ct + lo, out + lo, hi - lo);
     }
@@ -152,31 +142,30 @@ __global__ void __launch_bounds__(VM_BLOCK) pairing_vm_kernel(const uint64_t* __
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-// slot file of one block: slots x 2 halves x (pairings per block x 2 coordinates) x 16 B
-static int vm_smem_bytes(const kb_ctx* ctx) { return ctx->vm_slots * 2 * (VM_BLOCK / ctx->vm_width) * 16; }
+// slot file of one block: slots x 2 halves x threads x 16 B
+static int vm_smem_bytes(const kb_ctx* ctx) { return ctx->vm_slots * 2 * VM_BLOCK * 16; }
 
-// Program choice: KB_PAIRING_PROG="slots,width" (defaults to the fastest measured variant)
+// Program choice: KB_PAIRING_SLOTS (defaults to the fastest measured variant)
 void vm_init(kb_ctx* ctx) {
   using namespace vmprog;
-  int slots = 14, width = 1;
-  if (const char* e = getenv("KB_PAIRING_PROG")) sscanf(e, "%d,%d", &slots, &width);
+  int slots = 18;
+  if (const char* e = getenv("KB_PAIRING_SLOTS")) slots = atoi(e);
   const Program* pr = nullptr;
-  for (int k = 0; k < NUM_PROGRAMS; k++) if (PROGRAMS[k].slots == slots && PROGRAMS[k].width == width) pr = &PROGRAMS[k];
-  if (!pr) throw CudaError("KB_PAIRING_PROG names a program variant that was not generated");
+  for (int k = 0; k < NUM_PROGRAMS; k++) if (PROGRAMS[k].slots == slots) pr = &PROGRAMS[k];
+  if (!pr) throw CudaError("KB_PAIRING_SLOTS names a program variant that was not generated");
   ctx->vm_slots = pr->slots;
-  ctx->vm_width = pr->width;
   ctx->vm_gslots = pr->gslots;
   ctx->vm_out = 0;
   for (int k = 0; k < 6; k++) ctx->vm_out |= (uint64_t)pr->out[k] << (8 * k);
-  const size_t bytes = (size_t)(pr->len + pr->width) * 8;   // one padding bundle after END (prefetch)
+  const size_t bytes = (size_t)(pr->len + 2) * 8;   // one padding instruction after END (prefetch)
   KB_CUDA(cudaMalloc((void**)&ctx->d_vm_prog, bytes));
   KB_CUDA(cudaMemsetAsync(ctx->d_vm_prog, 0, bytes, ctx->stream));
   KB_CUDA(cudaMemcpyAsync(ctx->d_vm_prog, pr->words, (size_t)pr->len * 8, cudaMemcpyHostToDevice, ctx->stream));
   KB_CUDA(cudaMalloc((void**)&ctx->d_vm_consts, sizeof(CONSTS)));
   KB_CUDA(cudaMemcpyAsync(ctx->d_vm_consts, CONSTS, sizeof(CONSTS), cudaMemcpyHostToDevice, ctx->stream));
-  const int smem = vm_smem_bytes(ctx);
-  if (width == 1) KB_CUDA(cudaFuncSetAttribute(pairing_vm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  else KB_CUDA(cudaFuncSetAttribute(pairing_vm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  KB_CUDA(cudaFuncSetAttribute(pairing_vm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, vm_smem_bytes(ctx)));
+  KB_CUDA(cudaFuncSetAttribute(pairing_vm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, vm_smem_bytes(ctx)));
+  KB_CUDA(cudaFuncSetAttribute(pairing_vm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, vm_smem_bytes(ctx)));
 }
 
 void vm_free(kb_ctx* ctx) {
@@ -186,17 +175,16 @@ void vm_free(kb_ctx* ctx) {
 
 static void vm_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
                       uint64_t n, int mode, uint32_t* d_gt_words, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out) {
-  const int pairs_per_block = VM_BLOCK / (2 * ctx->vm_width);
-  const unsigned blocks = cdiv(n, pairs_per_block);
-  const uint64_t gstride = (uint64_t)blocks * pairs_per_block * 2;
-  DevBuf<uint4> scratch(ctx, (size_t)ctx->vm_gslots * 2 * gstride);
+  const unsigned blocks = cdiv(2 * n, VM_BLOCK);
+  const uint64_t gstride = (uint64_t)blocks * VM_BLOCK;
+  DevBuf<uint4> scratch(ctx, (size_t)(ctx->vm_gslots ? ctx->vm_gslots : 1) * 2 * gstride);
+  int minb = 227 * 1024 / (vm_smem_bytes(ctx) + 1024);   // blocks whose slot files fit one SM
+  if (const char* e = getenv("KB_PAIRING_MINB")) minb = atoi(e);
   timer_start(ctx, KB_T_PAIRING);
-  if (ctx->vm_width == 1)
-    KB_LAUNCH(ctx, pairing_vm_kernel<1>, blocks, VM_BLOCK, vm_smem_bytes(ctx), ctx->d_vm_prog, ctx->d_vm_consts,
-              ctx->vm_out, d_g1, d_g1_inf, d_g2, d_g2_inf, n, scratch.p, gstride, mode, d_gt_words, d_msg_ct, d_off, d_out);
-  else
-    KB_LAUNCH(ctx, pairing_vm_kernel<2>, blocks, VM_BLOCK, vm_smem_bytes(ctx), ctx->d_vm_prog, ctx->d_vm_consts,
-              ctx->vm_out, d_g1, d_g1_inf, d_g2, d_g2_inf, n, scratch.p, gstride, mode, d_gt_words, d_msg_ct, d_off, d_out);
+#define KB_VM_GO(MB) KB_LAUNCH(ctx, pairing_vm_kernel<MB>, blocks, VM_BLOCK, vm_smem_bytes(ctx), ctx->d_vm_prog, ctx->d_vm_consts, \
+            ctx->vm_out, d_g1, d_g1_inf, d_g2, d_g2_inf, n, scratch.p, gstride, mode, d_gt_words, d_msg_ct, d_off, d_out)
+  if (minb >= 4) KB_VM_GO(4); else if (minb == 3) KB_VM_GO(3); else KB_VM_GO(2);
+#undef KB_VM_GO
   timer_stop(ctx, KB_T_PAIRING);
 }
 

@@ -136,31 +136,27 @@ void he_gt_key(const uint8_t* gt384, const uint8_t* msg, uint8_t* out, uint64_t 
 
 }  // extern "C"
 
-// The pairing VM (pairing_vm.cuh) interpreting the shipped program (slots, width): GT as 384 canonical bytes.
-// Exactly the interpreter + program the GPU kernel runs; the 2 x width lanes of a pairing are host threads, the
-// shuffle exchange is a rendezvous of the two lanes of a half, and sync() is a barrier over all lanes.
+// The pairing VM (pairing_vm.cuh) interpreting the shipped program for `slots` slots: GT as 384 canonical bytes.
+// Exactly the interpreter + program the GPU kernel runs; the two lanes of a pairing are two host threads, the
+// shuffle exchange and sync() are rendezvous of the two.
 struct Barrier {
-  int n;
   std::atomic<int> arrived{0};
   std::atomic<int> gen{0};
-  explicit Barrier(int n_) : n(n_) {}
   void wait() {
     int g0 = gen.load();
-    if (arrived.fetch_add(1) == n - 1) { arrived.store(0); gen.fetch_add(1); }
+    if (arrived.fetch_add(1) == 1) { arrived.store(0); gen.fetch_add(1); }
     else while (gen.load() == g0) std::this_thread::yield();
   }
 };
 struct PairShared {
   Fq s[2][32];
   Fq g[2][256];
-  Fq box[2][2];
-  Barrier all;
-  Barrier half[2] = {Barrier(2), Barrier(2)};
-  explicit PairShared(int lanes) : all(lanes) {}
+  Fq box[2];
+  Barrier bar;
 };
 struct HostLane {
   PairShared* sh;
-  uint32_t t, h;
+  uint32_t t;
   Fq ld(uint32_t i) const { return sh->s[t][i]; }
   Fq ld_partner(uint32_t i) const { return sh->s[1 - t][i]; }
   void st(uint32_t i, const Fq& v) { sh->s[t][i] = v; }
@@ -168,50 +164,41 @@ struct HostLane {
   void stg(uint32_t i, const Fq& v) { sh->g[t][i] = v; }
   Fq ldc(const uint32_t* p) const { return ldq(p + 8 * t); }
   Fq xchg(const Fq& v) {
-    sh->box[h][t] = v;
-    sh->half[h].wait();
-    Fq r = sh->box[h][1 - t];
-    sh->half[h].wait();
+    sh->box[t] = v;
+    sh->bar.wait();
+    Fq r = sh->box[1 - t];
+    sh->bar.wait();
     return r;
   }
-  void sync() { sh->all.wait(); }
+  void sync() { sh->bar.wait(); }
 };
-template <int W>
-static void vm_host_lane(PairShared* sh, uint32_t h, uint32_t t, const uint64_t* prog, const uint8_t* outs,
+static void vm_host_lane(PairShared* sh, uint32_t t, const uint64_t* prog, const uint8_t* outs,
                          const uint32_t* p_xy, const uint32_t* q_xy, uint32_t* w) {
-  HostLane ln{sh, t, h};
-  if (h == 0) {
-    ln.st(0, ldq(p_xy + 8 * t));
-    ln.st(1, ldq(q_xy + 8 * t));
-    ln.st(2, ldq(q_xy + 16 + 8 * t));
+  HostLane ln{sh, t};
+  ln.st(0, ldq(p_xy + 8 * t));
+  ln.st(1, ldq(q_xy + 8 * t));
+  ln.st(2, ldq(q_xy + 16 + 8 * t));
+  vm::run(prog, ln, vmprog::CONSTS);
+  ln.sync();
+  for (int k = 0; k < 6; k++) {
+    Fq c = fp_from_mont<FqParams>(ln.ld(outs[k]));
+    for (int j = 0; j < 8; j++) w[16 * k + 8 * t + j] = c.v[j];
   }
-  ln.sync();
-  vm::run<W>(prog, ln, vmprog::CONSTS);
-  ln.sync();
-  if (h == 0)
-    for (int k = 0; k < 6; k++) {
-      Fq c = fp_from_mont<FqParams>(ln.ld(outs[k]));
-      for (int j = 0; j < 8; j++) w[16 * k + 8 * t + j] = c.v[j];
-    }
 }
+
 extern "C" {
 
-int he_vm_pairing_bytes(int slots, int width, const uint32_t* p_xy, const uint32_t* q_xy, uint8_t* out384) {
+int he_vm_pairing_bytes(int slots, const uint32_t* p_xy, const uint32_t* q_xy, uint8_t* out384) {
   const vmprog::Program* pr = nullptr;
-  for (int k = 0; k < vmprog::NUM_PROGRAMS; k++)
-    if (vmprog::PROGRAMS[k].slots == slots && vmprog::PROGRAMS[k].width == width) pr = &vmprog::PROGRAMS[k];
+  for (int k = 0; k < vmprog::NUM_PROGRAMS; k++) if (vmprog::PROGRAMS[k].slots == slots) pr = &vmprog::PROGRAMS[k];
   if (!pr) return -1;
   std::vector<uint64_t> padded(pr->words, pr->words + pr->len);
-  for (int k = 0; k < width; k++) padded.push_back(0);
-  PairShared* sh = new PairShared(2 * width);
+  padded.push_back(0); padded.push_back(0);
+  PairShared* sh = new PairShared();
   uint32_t w[96];
-  std::vector<std::thread> th;
-  for (uint32_t h = 0; h < (uint32_t)width; h++)
-    for (uint32_t t = 0; t < 2; t++) {
-      if (width == 1) th.emplace_back(vm_host_lane<1>, sh, h, t, padded.data(), pr->out, p_xy, q_xy, w);
-      else th.emplace_back(vm_host_lane<2>, sh, h, t, padded.data(), pr->out, p_xy, q_xy, w);
-    }
-  for (auto& x : th) x.join();
+  std::thread other(vm_host_lane, sh, 1u, padded.data(), pr->out, p_xy, q_xy, w);
+  vm_host_lane(sh, 0u, padded.data(), pr->out, p_xy, q_xy, w);
+  other.join();
   memcpy(out384, w, 384);
   delete sh;
   return pr->len;

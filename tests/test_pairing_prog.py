@@ -36,22 +36,26 @@ def _cases(n):
     return out
 
 
-@pytest.mark.parametrize("slots,width", [(14, 1), (20, 1), (28, 1), (28, 2), (18, 2)])
-def test_simulated_program_matches_oracle(slots, width):
-    words, gcount, outs, st = gp.build("pairing", slots, width)
+@pytest.mark.parametrize("slots,macros", [(14, True), (18, True), (28, True), (14, False)])
+def test_simulated_program_matches_oracle(slots, macros):
+    gp.USE_MACROS = macros
+    try:
+        words, gcount, outs, st = gp.build("pairing", slots)
+    finally:
+        gp.USE_MACROS = True
     assert st["fq_muls"] < 18000 and all(s < slots for s in outs)
     for p, q in _cases(1):
-        got = gp.simulate(words, slots, outs, [(p[0], p[1]), q[0], q[1]], width)
+        got = gp.simulate(words, slots, outs, [(p[0], p[1]), q[0], q[1]])
         assert got == _flat(bn.pairing(p, q))
 
 
 def test_generated_header_is_current():
     path = os.path.join(ROOT, "keaki_b200", "csrc", "pairing_prog_gen.cuh")
     text = open(path).read()
-    for what, slots, width in gp.VARIANTS:
-        words, gcount, outs, st = gp.build(what, slots, width)
-        name = gp.variant_name(what, slots, width)
-        assert "{%d, %d, %d, %d, {%s}, %s_WORDS}" % (slots, width, gcount, len(words), ", ".join(map(str, outs)), name) in text
+    for what, slots in gp.VARIANTS:
+        words, gcount, outs, st = gp.build(what, slots)
+        name = gp.variant_name(what, slots)
+        assert "{%d, %d, %d, {%s}, %s_WORDS}" % (slots, gcount, len(words), ", ".join(map(str, outs)), name) in text
         assert "0x%016xull" % words[len(words) // 2] in text
 
 
@@ -62,11 +66,11 @@ def test_constants_match_oracle():
     assert sum(d << i for i, d in enumerate(gp.Z_NAF)) == bn.Z
 
 
-@pytest.mark.parametrize("slots,width", [(14, 1), (9, 1), (28, 2), (18, 2)])
-def test_hostemu_interpreter_matches_oracle(slots, width):
+@pytest.mark.parametrize("slots", [14, 28])
+def test_hostemu_interpreter_matches_oracle(slots):
     for p, q in _cases(2):
         out = (ctypes.c_uint8 * 384)()
-        n = he.he_vm_pairing_bytes(slots, width, P(L.g1_m(p)), P(L.g2_m(q)), out)
+        n = he.he_vm_pairing_bytes(slots, P(L.g1_m(p)), P(L.g2_m(q)), out)
         assert n > 1000
         assert bytes(out) == bn.gt_to_bytes(bn.pairing(p, q))
 

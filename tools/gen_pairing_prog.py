@@ -28,26 +28,34 @@ ATE = [0, 0, 0, 1, 0, 1, 0, -1, 0, 0, 1, -1, 0, 0, 1, 0, 0, 1, 1, 0, -1, 0, 0, 1
 assert sum(d << i for i, d in enumerate(ATE)) == 6 * Z + 2
 
 # ---------------------------------------------------------------------------------------------
-# VM instruction set.  One 64-bit word:
-#   op | dst << 8 | A1 << 16 | A2 << 24 | B1 << 32 | B2 << 40 | F << 48 | G << 56
+# VM instruction set.  One instruction = two 64-bit words:
+#   w0 = op | dst << 8 | A1 << 16 | A2 << 24 | B1 << 32 | B2 << 40 | F << 48 | G << 56
+#   w1 = X0 | X1 << 8 | ... | X7 << 56                       (extra slot numbers of the macro operations)
 # An operand byte is  slot | code << 5  (0xFF = absent); the code applies a cheap linear map while
 # the operand is fetched: +x, -x, 2x, -2x, xi x, -xi x, 3x, 3 xi x (slot 31 is never used, so 0xFF is free).
-#   MULX : dst = (A1 + A2) * (B1 + B2) + F + G        (Fq2 product, Karatsuba)
+#   MULX : dst = (A1 + A2) * (B1 + B2) + F + G        (Fq2 product)
 #   SQRX : dst = (A1 + A2)^2 + F + G
 #   MULF0: dst = (A1 + A2) * (B1).c0 + F + G          (Fq2 times an Fq scalar held in half a slot)
 #   MULF1: dst = (A1 + A2) * (B1).c1 + F + G
 #   LIN  : dst = A1 + A2 + B1 + B2 + F + G
 #   CONJ : dst = conj(A1 + A2);   INV: dst = 1 / (A1 + A2)
 #   LDC  : dst = constant[A1 | A2 << 8];  LDG: dst = global[A1 | A2 << 8];  STG: global[A1 | A2 << 8] = slot B1
+# Macro operations (plain slot numbers, no codes) keep their intermediates in registers - no slot
+# traffic, decoding or operand mapping per inner product:
+#   F6MUL : (dst, X0, X1) = (A1, A2, B1) * (B2, F, G) in Fq6 = Fq2[v]/(v^3 - xi)            6 products
+#   CYCSQR: (dst, X0..X4) = (A1, A2, B1, B2, F, G)^2 for a cyclotomic Fq12 element, w-basis    9 squarings
+#   F6M01 : (dst, X0, X1) = (A1, A2, B1) * (B2 + F v)                                          5 products
+#   F6SCL : (dst, X0, X1) = (A1, A2, B1) * B2   (Fq6 times an Fq2 scalar)                      3 products
 # ---------------------------------------------------------------------------------------------
-OPS = ["END", "MULX", "SQRX", "MULF0", "MULF1", "LIN", "CONJ", "INV", "LDC", "LDG", "STG", "NOP"]
+OPS = ["END", "MULX", "SQRX", "MULF0", "MULF1", "LIN", "CONJ", "INV", "LDC", "LDG", "STG", "NOP", "F6MUL", "CYCSQR", "F6M01", "F6SCL"]
 OP = {n: i for i, n in enumerate(OPS)}
+MACROS = ("F6MUL", "CYCSQR", "F6M01", "F6SCL")
 # operand codes: coefficient (a, b) meaning a + b xi
 CODES = [(1, 0), (-1, 0), (2, 0), (-2, 0), (0, 1), (0, -1), (3, 0), (0, 3)]
 CODE = {c: i for i, c in enumerate(CODES)}
 ABSENT = 0xFF
 # cost in Fq multiplications (for the statistics printed into the header)
-FQ_MULS = {"MULX": 3, "SQRX": 2, "MULF0": 2, "MULF1": 2, "INV": 2 + 2 + 314}
+FQ_MULS = {"MULX": 3, "SQRX": 2, "MULF0": 2, "MULF1": 2, "INV": 2 + 2 + 314, "F6MUL": 18, "CYCSQR": 18, "F6M01": 15, "F6SCL": 9}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -97,14 +105,19 @@ C_TWY = _const("tw_y", f2_pow(XI, (Q - 1) // 2))
 # operand fetch and anything larger is first materialised by a LIN instruction.
 # ---------------------------------------------------------------------------------------------
 class Ins:
-    __slots__ = ("op", "dst", "opnds", "imm")
+    __slots__ = ("op", "dsts", "opnds", "extra", "imm")
 
-    def __init__(self, op, dst, opnds=(), imm=0):
-        self.op, self.dst, self.imm = op, dst, imm
+    def __init__(self, op, dsts, opnds=(), imm=0, extra=()):
+        self.op, self.dsts, self.imm = op, list(dsts), imm
         self.opnds = list(opnds) + [None] * (6 - len(opnds))   # A1 A2 B1 B2 F G: (id, code) or None
+        self.extra = list(extra)                                # further source ids of a macro operation
+
+    @property
+    def dst(self):
+        return self.dsts[0]
 
     def srcs(self):
-        return [o[0] for o in self.opnds if o is not None]
+        return [o[0] for o in self.opnds if o is not None] + self.extra
 
 
 class Trace:
@@ -122,8 +135,23 @@ class Trace:
 
     def emit(self, op, opnds=(), imm=0):
         d = self.new()
-        self.ins.append(Ins(op, d, opnds, imm))
+        self.ins.append(Ins(op, [d], opnds, imm))
         return d
+
+    def emit_macro(self, op, srcs, ndst):
+        """srcs: materialised single-term values (V); returns ndst new values"""
+        ids = []
+        for x in srcs:
+            x = x.mat()
+            if x.is_zero():
+                x = zero_value(self)
+            (vid, c), = x.terms.items()
+            assert c == (1, 0)
+            ids.append(vid)
+        dsts = [self.new() for _ in range(ndst)]
+        plain = CODE[(1, 0)]
+        self.ins.append(Ins(op, dsts, [(v, plain) for v in ids[:6]], extra=ids[6:]))
+        return [V.of(self, d) for d in dsts]
 
 
 def _decompose(c):
@@ -240,6 +268,13 @@ class V:
         return V.of(self.t, self.t.emit("INV", self.fold()))
 
 
+def zero_value(t):
+    """a materialised zero (the lazy zero has no terms and no slot)"""
+    one = const(t, C_ONE)
+    oid = next(iter(one.terms))
+    return V.of(t, t.emit("LIN", [(oid, CODE[(1, 0)]), (oid, CODE[(-1, 0)])]))
+
+
 def const(t, idx):
     if idx == C_ZERO:
         return V(t, {})
@@ -258,7 +293,12 @@ def f6_neg(a): return tuple(-x for x in a)
 def f6_mul_v(a): return (a[2].mulxi(), a[0], a[1])
 
 
+USE_MACROS = True
+
+
 def f6_mul(a, b):
+    if USE_MACROS and not any(x.is_zero() for x in a + b):
+        return tuple(a[0].t.emit_macro("F6MUL", list(a) + list(b), 3))
     v0, v1, v2 = a[0] * b[0], a[1] * b[1], a[2] * b[2]
     c0 = v0 + ((a[1] + a[2]) * (b[1] + b[2]) - v1 - v2).mulxi()
     c1 = ((a[0] + a[1]) * (b[0] + b[1]) - v0 - v1).mat() + v2.mulxi()
@@ -275,10 +315,15 @@ def f6_sqr(a):  # Chung-Hasan SQR2
     return (s0 + s3.mulxi(), s1 + s4.mulxi(), s1 + s2 + s3 - s0 - s4)
 
 
-def f6_mul_f2(a, k): return (a[0] * k, a[1] * k, a[2] * k)
+def f6_mul_f2(a, k):
+    if USE_MACROS and not any(x.is_zero() for x in a) and not k.is_zero():
+        return tuple(a[0].t.emit_macro("F6SCL", list(a) + [k], 3))
+    return (a[0] * k, a[1] * k, a[2] * k)
 
 
 def f6_mul_01(a, b0, b1):  # a * (b0 + b1 v)
+    if USE_MACROS and not any(x.is_zero() for x in a) and not b0.is_zero() and not b1.is_zero():
+        return tuple(a[0].t.emit_macro("F6M01", list(a) + [b0, b1], 3))
     aa, bb = a[0] * b0, a[1] * b1
     c0 = ((a[1] + a[2]) * b1 - bb).mulxi() + aa
     c1 = ((a[0] + a[1]) * (b0 + b1) - aa - bb).mat()
@@ -343,6 +388,8 @@ def fq4_sqr(a, b):
 
 
 def cyclotomic_sqr(g):  # Granger-Scott; same arrangement as tower.cuh (checked there)
+    if USE_MACROS:
+        return g[0].t.emit_macro("CYCSQR", g, 6)
     A0, A1 = fq4_sqr(g[0], g[3])
     B0, B1 = fq4_sqr(g[1], g[4])
     C0, C1 = fq4_sqr(g[2], g[5])
@@ -527,8 +574,7 @@ def trace_pairing(what="pairing"):
     for x in c0 + c1:
         x = x.mat()
         if x.is_zero():
-            x = V.of(t, t.emit("LIN", [(const(t, C_ONE).mat().code_terms()[0][0], CODE[(1, 0)]),
-                                        (const(t, C_ONE).mat().code_terms()[0][0], CODE[(-1, 0)])]))
+            x = zero_value(t)
         t.outputs.append(next(iter(x.terms)))
     return t
 
@@ -544,7 +590,7 @@ def fuse_posts(t):
             use_count[s_] = use_count.get(s_, 0) + 1
     for o in t.outputs:
         use_count[o] = use_count.get(o, 0) + 1
-    defs = {i.dst: i for i in t.ins}
+    defs = {i.dst: i for i in t.ins if len(i.dsts) == 1}
     dead = set()
     for L in t.ins:
         if L.op != "LIN":
@@ -568,96 +614,39 @@ def eliminate_dead(t):
     live = set(t.outputs)
     keep = []
     for ins in reversed(t.ins):
-        if ins.dst in live:
+        if any(d in live for d in ins.dsts):
             keep.append(ins)
             live.update(ins.srcs())
     t.ins = keep[::-1]
 
 
-def encode(op, dst=0, ob=(ABSENT,) * 6):
-    w = OP[op] | (dst << 8)
+def encode(op, dst=0, ob=(ABSENT,) * 6, xb=()):
+    """-> (w0, w1)"""
+    w0 = OP[op] | (dst << 8)
     for k, b in enumerate(ob):
-        w |= b << (16 + 8 * k)
-    return w
+        w0 |= b << (16 + 8 * k)
+    w1 = 0
+    xb = list(xb) + [ABSENT] * (8 - len(xb))
+    for k, b in enumerate(xb):
+        w1 |= b << (8 * k)
+    return (w0, w1)
 
 
-COST = {"MULX": 3, "SQRX": 2, "MULF0": 2, "MULF1": 2, "LIN": 1, "CONJ": 1, "INV": 320}
-
-
-def signature(i):
-    return (i.op,) + tuple(None if o is None else o[1] for o in i.opnds)
-
-
-def schedule(t, width, window):
-    """List-schedules the trace into bundles of `width` (1 or 2) independent instructions of the same
-    opcode (the two halves of a warp execute one bundle in lockstep; equal opcodes keep them on one
-    code path, equal operand codes are preferred for the same reason).  Only the first `window`
-    unscheduled instructions are candidates, which bounds the reordering and with it the slot pressure.
-    Returns a list of tuples of Ins."""
-    real = [i for i in t.ins if i.op != "LDC"]
-    consts = {i.dst for i in t.ins if i.op == "LDC"}
-    if width == 1:
-        return [(i,) for i in real]
-    prod = {i.dst: k for k, i in enumerate(real)}
-    n = len(real)
-    deps = [[prod[s_] for s_ in set(i.srcs()) if s_ in prod] for i in real]
-    users = [[] for _ in range(n)]
-    for k, d in enumerate(deps):
-        for j in d:
-            users[j].append(k)
-    prio = [0] * n
-    for k in range(n - 1, -1, -1):
-        prio[k] = COST[real[k].op] + max([prio[u] for u in users[k]], default=0)
-    done_at = [None] * n      # bundle index in which instruction k was issued
-    bundles = []
-    first = 0
-    while first < n:
-        while first < n and done_at[first] is not None:
-            first += 1
-        if first >= n:
-            break
-        b = len(bundles)
-        cand = []
-        k, seen = first, 0
-        while k < n and seen < window:
-            if done_at[k] is None:
-                seen += 1
-                if all(done_at[j] is not None and done_at[j] < b for j in deps[k]):
-                    cand.append(k)
-            k += 1
-        # the oldest unscheduled instruction is always ready (its producers are older): take the most critical candidate
-        x = max(cand, key=lambda k_: (prio[k_], -k_))
-        sig = signature(real[x])
-        best, bk = None, None
-        for k_ in cand:
-            if k_ == x or real[k_].op != real[x].op or real[k_].op == "INV":
-                continue
-            key = (signature(real[k_]) == sig, prio[k_], -k_)
-            if bk is None or key > bk:
-                best, bk = k_, key
-        done_at[x] = b
-        if best is None:
-            bundles.append((real[x],))
-        else:
-            done_at[best] = b
-            bundles.append((real[x], real[best]))
-    return bundles
-
-
-def allocate(t, nslots, width=1, window=48):
-    """Returns (words, n_global_slots, out_slots, stats): `width` words per bundle.
-    Slots 0..len(inputs)-1 hold the inputs."""
+def allocate(t, nslots):
+    """Returns (words, n_global_slots, out_slots, stats): two 64-bit words per instruction.
+    Slots 0..len(inputs)-1 hold the inputs.  Every lane reads all operands of an instruction before any lane
+    stores a result (the interpreter synchronises in between), so destinations may reuse the slots of sources
+    that die at the instruction."""
     assert nslots <= 31
-    bundles = schedule(t, width, window)
+    real = [i for i in t.ins if i.op != "LDC"]
     const_of = {i.dst: i.imm for i in t.ins if i.op == "LDC"}
     INF = 1 << 60
     uses = {}
-    for pos, bd in enumerate(bundles):
-        for i in bd:
-            for s_ in i.srcs():
-                uses.setdefault(s_, []).append(pos)
+    for pos, i in enumerate(real):
+        for s_ in i.srcs():
+            uses.setdefault(s_, []).append(pos)
     for o in t.outputs:
-        uses.setdefault(o, []).append(len(bundles))
+        uses.setdefault(o, []).append(len(real))
     ptr = {v: 0 for v in uses}
 
     def next_use(v, pos):
@@ -675,12 +664,8 @@ def allocate(t, nslots, width=1, window=48):
     for k, v in enumerate(t.inputs):
         slot_of[v] = k
         val_in[k] = v
-    out = []          # list of bundles of encoded words (each exactly `width` long)
+    out = []
     stats = {"spill_st": 0, "spill_ld": 0}
-    NOP = encode("NOP")
-
-    def emit1(w):
-        out.append([w] + [NOP] * (width - 1))
 
     def release(v):
         s_ = slot_of.pop(v)
@@ -710,7 +695,7 @@ def allocate(t, nslots, width=1, window=48):
             if g == gcount:
                 gcount += 1
             gslot_of[v] = g
-            emit1(encode("STG", 0, (g & 255, g >> 8, best, ABSENT, ABSENT, ABSENT)))
+            out.append(encode("STG", 0, (g & 255, g >> 8, best, ABSENT, ABSENT, ABSENT)))
             stats["spill_st"] += 1
         del slot_of[v]
         val_in[best] = None
@@ -722,60 +707,52 @@ def allocate(t, nslots, width=1, window=48):
         s_ = get_slot(pos, pinned)
         if v in const_of:
             c = const_of[v]
-            emit1(encode("LDC", s_, (c & 255, c >> 8, ABSENT, ABSENT, ABSENT, ABSENT)))
+            out.append(encode("LDC", s_, (c & 255, c >> 8, ABSENT, ABSENT, ABSENT, ABSENT)))
         else:
             g = gslot_of[v]
-            emit1(encode("LDG", s_, (g & 255, g >> 8, ABSENT, ABSENT, ABSENT, ABSENT)))
+            out.append(encode("LDG", s_, (g & 255, g >> 8, ABSENT, ABSENT, ABSENT, ABSENT)))
             stats["spill_ld"] += 1
         slot_of[v] = s_
         val_in[s_] = v
         return s_
 
-    full = 0
-    same_sig = 0
-    for pos, bd in enumerate(bundles):
-        pinned = set()
-        for i in bd:
-            pinned.update(i.srcs())
+    for pos, i in enumerate(real):
+        pinned = set(i.srcs())
         for v in sorted(pinned):
             ensure(v, pos, pinned)
-        obs = [[ABSENT if o is None else (slot_of[o[0]] | (o[1] << 5)) for o in i.opnds] for i in bd]
-        # every lane reads its operands before any lane stores (the interpreter synchronises in between), so a
-        # destination may reuse the slot of a source that dies in this bundle
+        ob = [ABSENT if o is None else (slot_of[o[0]] | (o[1] << 5)) for o in i.opnds]
+        xsrc = [slot_of[v] for v in i.extra]
         for v in sorted(pinned):
             if next_use(v, pos + 1) == INF:
                 release(v)
-        words = []
         pin2 = set(pinned)
-        for i, ob in zip(bd, obs):
-            ds = get_slot(pos + 1, pin2)
-            slot_of[i.dst] = ds
-            val_in[ds] = i.dst
-            pin2.add(i.dst)
-            words.append(encode(i.op, ds, ob))
-        if len(bd) > 1:
-            full += 1
-            same_sig += signature(bd[0]) == signature(bd[1])
-        out.append(words + [NOP] * (width - len(words)))
+        ds = []
+        for d in i.dsts:
+            sl = get_slot(pos + 1, pin2)
+            slot_of[d] = sl
+            val_in[sl] = d
+            pin2.add(d)
+            ds.append(sl)
+        out.append(encode(i.op, ds[0], ob, xsrc + ds[1:]))
+        for d in i.dsts:   # results nobody reads (a macro operation always produces all of its outputs)
+            if next_use(d, pos + 1) == INF:
+                release(d)
     pinned = set(t.outputs)
-    out_slots = [ensure(v, len(bundles), pinned) for v in t.outputs]
-    out.append([encode("END")] * width)
-    flat = [w for bd in out for w in bd]
-    stats["n_bundles"] = len(out)
-    stats["full_bundles"] = full
-    stats["same_signature"] = same_sig
-    stats["fq_muls"] = sum(FQ_MULS.get(OPS[w & 255], 0) for w in flat)
-    # critical resource: per bundle the halves run side by side, so the cost is the max over the halves
-    stats["bundle_cost"] = sum(max(COST.get(OPS[w & 255], 0.3) for w in bd) for bd in out)
+    out_slots = [ensure(v, len(real), pinned) for v in t.outputs]
+    out.append(encode("END"))
+    flat = [w for pair in out for w in pair]
+    stats["n_ins"] = len(out)
+    stats["fq_muls"] = sum(FQ_MULS.get(OPS[w0 & 255], 0) for w0, _ in out)
     hist = {}
-    for w in flat:
-        hist[OPS[w & 255]] = hist.get(OPS[w & 255], 0) + 1
+    for w0, _ in out:
+        hist[OPS[w0 & 255]] = hist.get(OPS[w0 & 255], 0) + 1
     stats["hist"] = hist
     return flat, gcount, out_slots, stats
 
 
 # ---------------------------------------------------------------------------------------------
-# simulator (plain integers, canonical values) - used by the tests
+# simulator (plain integers, canonical values) - used by the tests.  The macro operations are
+# evaluated as plain polynomial arithmetic over Fq2, independently of the formulas above.
 # ---------------------------------------------------------------------------------------------
 def _apply(code, x):
     a, b = CODES[code]
@@ -786,61 +763,89 @@ def _apply(code, x):
     return r
 
 
-def simulate(words, nslots, out_slots, inputs, width=1):
-    """inputs: list of Fq2 (tuples of ints) for slots 0..; returns the Fq2 values of out_slots.
-    The instructions of a bundle read the slot file as it was before the bundle."""
+def _f2_add(x, y): return ((x[0] + y[0]) % Q, (x[1] + y[1]) % Q)
+
+
+def _polymul_mod(a, b, n):
+    """(sum a_i X^i)(sum b_j X^j) mod X^n - xi over Fq2"""
+    r = [(0, 0)] * n
+    for i, x in enumerate(a):
+        for j, y in enumerate(b):
+            pr = f2_mul(x, y)
+            k = i + j
+            while k >= n:
+                pr = f2_mul(pr, XI)
+                k -= n
+            r[k] = _f2_add(r[k], pr)
+    return r
+
+
+def simulate(words, nslots, out_slots, inputs):
+    """inputs: list of Fq2 (tuples of ints) for slots 0..; returns the Fq2 values of out_slots."""
     S = [(0, 0)] * 32
     G = {}
     for k, v in enumerate(inputs):
         S[k] = v
-
-    def add(x, y): return ((x[0] + y[0]) % Q, (x[1] + y[1]) % Q)
-
-    for base in range(0, len(words), width):
-        bundle = words[base:base + width]
-        if OPS[bundle[0] & 255] == "END":
+    for base in range(0, len(words), 2):
+        w, w1 = words[base], words[base + 1]
+        op, d = OPS[w & 255], (w >> 8) & 255
+        ob = [(w >> (16 + 8 * k)) & 255 for k in range(6)]
+        xb = [(w1 >> (8 * k)) & 255 for k in range(8)]
+        if op == "END":
             break
-        writes = []
-        for w in bundle:
-            op, d = OPS[w & 255], (w >> 8) & 255
-            ob = [(w >> (16 + 8 * k)) & 255 for k in range(6)]
-            if op == "NOP":
-                continue
-            if op == "LDC":
-                writes.append((d, CONSTS[ob[0] | (ob[1] << 8)]))
-                continue
-            if op == "LDG":
-                writes.append((d, G[ob[0] | (ob[1] << 8)]))
-                continue
-            if op == "STG":
-                G[ob[0] | (ob[1] << 8)] = S[ob[2]]
-                continue
-            assert d < nslots and all(b == ABSENT or (b & 31) < nslots for b in ob)
-            val = [(0, 0) if b == ABSENT else _apply(b >> 5, S[b & 31]) for b in ob]
-            A, B = add(val[0], val[1]), add(val[2], val[3])
-            if op == "MULX": r = f2_mul(A, B)
-            elif op == "SQRX": r = f2_mul(A, A)
-            elif op == "MULF0": r = (A[0] * S[ob[2] & 31][0] % Q, A[1] * S[ob[2] & 31][0] % Q)
-            elif op == "MULF1": r = (A[0] * S[ob[2] & 31][1] % Q, A[1] * S[ob[2] & 31][1] % Q)
-            elif op == "LIN": r = add(A, B)
-            elif op == "CONJ": r = (A[0], -A[1] % Q)
-            elif op == "INV": r = f2_inv(A) if A != (0, 0) else (0, 0)
+        if op == "NOP":
+            continue
+        if op == "LDC":
+            S[d] = CONSTS[ob[0] | (ob[1] << 8)]
+            continue
+        if op == "LDG":
+            S[d] = G[ob[0] | (ob[1] << 8)]
+            continue
+        if op == "STG":
+            G[ob[0] | (ob[1] << 8)] = S[ob[2]]
+            continue
+        assert d < nslots and all(b == ABSENT or (b & 31) < nslots for b in ob)
+        if op in MACROS:
+            assert all(b == ABSENT or b >> 5 == 0 for b in ob)
+            src = [None if b == ABSENT else S[b] for b in ob]
+            if op == "F6MUL":
+                res = _polymul_mod(src[:3], src[3:], 3)
+                dsts = [d, xb[0], xb[1]]
+            elif op == "CYCSQR":
+                res = _polymul_mod(src, src, 6)
+                dsts = [d] + xb[:5]
+            elif op == "F6M01":
+                res = _polymul_mod(src[:3], [src[3], src[4], (0, 0)], 3)
+                dsts = [d, xb[0], xb[1]]
             else:
-                raise ValueError(op)
-            if op in ("MULX", "SQRX", "MULF0", "MULF1", "LIN"):
-                r = add(add(r, val[4]), val[5])
-            writes.append((d, r))
-        assert len({d for d, _ in writes}) == len(writes)
-        for d, r in writes:
-            S[d] = r
+                res = _polymul_mod(src[:3], [src[3]], 3)
+                dsts = [d, xb[0], xb[1]]
+            assert len(set(dsts)) == len(dsts) and all(x < nslots for x in dsts)
+            for k, x in zip(dsts, res):
+                S[k] = x
+            continue
+        val = [(0, 0) if b == ABSENT else _apply(b >> 5, S[b & 31]) for b in ob]
+        A, B = _f2_add(val[0], val[1]), _f2_add(val[2], val[3])
+        if op == "MULX": r = f2_mul(A, B)
+        elif op == "SQRX": r = f2_mul(A, A)
+        elif op == "MULF0": r = (A[0] * S[ob[2] & 31][0] % Q, A[1] * S[ob[2] & 31][0] % Q)
+        elif op == "MULF1": r = (A[0] * S[ob[2] & 31][1] % Q, A[1] * S[ob[2] & 31][1] % Q)
+        elif op == "LIN": r = _f2_add(A, B)
+        elif op == "CONJ": r = (A[0], -A[1] % Q)
+        elif op == "INV": r = f2_inv(A) if A != (0, 0) else (0, 0)
+        else:
+            raise ValueError(op)
+        if op in ("MULX", "SQRX", "MULF0", "MULF1", "LIN"):
+            r = _f2_add(_f2_add(r, val[4]), val[5])
+        S[d] = r
     return [S[s_] for s_ in out_slots]
 
 
-def build(what, nslots, width=1, window=48):
+def build(what, nslots):
     t = trace_pairing(what)
     fuse_posts(t)
     eliminate_dead(t)
-    return allocate(t, nslots, width, window)
+    return allocate(t, nslots)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -850,19 +855,20 @@ def limbs(x):
     return ", ".join("0x%08xu" % ((x >> (32 * i)) & 0xFFFFFFFF) for i in range(8))
 
 
-# (what, slots, bundle width): the kernel picks by (slots, width)
-VARIANTS = [("pairing", 14, 1), ("pairing", 11, 1), ("pairing", 9, 1), ("pairing", 28, 1), ("pairing", 28, 2), ("pairing", 18, 2)]
+# (what, slots): the kernel picks by slot count
+VARIANTS = [("pairing", 14), ("pairing", 18), ("pairing", 28)]
 
 
-def variant_name(what, ns, width):
-    return "%s_S%d_W%d" % (what.upper(), ns, width)
+def variant_name(what, ns):
+    return "%s_S%d" % (what.upper(), ns)
 
 
 def main():
     out = ["// GENERATED by tools/gen_pairing_prog.py - do not edit.",
-           "// Straight-line Fq2 programs for the pairing VM (pairing_vm.cuh): optimal-ate Miller loop + arkworks final",
-           "// exponentiation, scheduled into bundles of W instructions and slot-allocated for S shared-memory slots.",
-           "// Word = op | dst<<8 | A1<<16 | A2<<24 | B1<<32 | B2<<40 | F<<48 | G<<56; operand = slot | code<<5, 0xFF absent.",
+           "// Straight-line programs for the pairing VM (pairing_vm.cuh): optimal-ate Miller loop + arkworks final",
+           "// exponentiation, slot-allocated for S shared-memory slots per pairing.  Two 64-bit words per instruction:",
+           "// w0 = op | dst<<8 | A1<<16 | A2<<24 | B1<<32 | B2<<40 | F<<48 | G<<56 (operand = slot | code<<5, 0xFF absent),",
+           "// w1 = eight further slot numbers of the macro operations.",
            "#pragma once", "#include <stdint.h>", "namespace kb { namespace vmprog {",
            "enum Op : uint32_t { " + ", ".join("OP_%s = %d" % (n, i) for i, n in enumerate(OPS)) + " };",
            "// operand codes: " + ", ".join("%d: %+d%+dxi" % (i, a, b) for i, (a, b) in enumerate(CODES)),
@@ -872,24 +878,23 @@ def main():
     for c in CONSTS:
         out.append("    " + limbs(c[0] * MONT % Q) + ", " + limbs(c[1] * MONT % Q) + ",")
     out.append("};")
-    out.append("struct Program { int slots, width, gslots, len; uint8_t out[6]; const uint64_t* words; };")
+    out.append("struct Program { int slots, gslots, len; uint8_t out[6]; const uint64_t* words; };  // len in 64-bit words")
     names = []
-    for what, ns, width in VARIANTS:
-        words, gcount, out_slots, st = build(what, ns, width)
-        name = variant_name(what, ns, width)
-        names.append((name, ns, width, gcount, len(words), out_slots))
-        out.append("// %s: %d bundles (%d full, %d with equal operand shapes), %d Fq multiplications, %d spill stores / "
-                   "%d spill loads, %d global slots; %s"
-                   % (name, st["n_bundles"], st["full_bundles"], st["same_signature"], st["fq_muls"], st["spill_st"],
-                      st["spill_ld"], gcount, " ".join("%s=%d" % kv for kv in sorted(st["hist"].items()))))
+    for what, ns in VARIANTS:
+        words, gcount, out_slots, st = build(what, ns)
+        name = variant_name(what, ns)
+        names.append((name, ns, gcount, len(words), out_slots))
+        out.append("// %s: %d instructions, %d Fq multiplications, %d spill stores / %d spill loads, %d global slots; %s"
+                   % (name, st["n_ins"], st["fq_muls"], st["spill_st"], st["spill_ld"], gcount,
+                      " ".join("%s=%d" % kv for kv in sorted(st["hist"].items()))))
         out.append("static const uint64_t %s_WORDS[%d] = {" % (name, len(words)))
         for i in range(0, len(words), 6):
             out.append("    " + ", ".join("0x%016xull" % w for w in words[i:i + 6]) + ",")
         out.append("};")
         print(name, st, "gslots", gcount, file=sys.stderr)
     out.append("static const Program PROGRAMS[%d] = {" % len(names))
-    for name, ns, width, gcount, ln, outs in names:
-        out.append("    {%d, %d, %d, %d, {%s}, %s_WORDS}," % (ns, width, gcount, ln, ", ".join(str(s_) for s_ in outs), name))
+    for name, ns, gcount, ln, outs in names:
+        out.append("    {%d, %d, %d, {%s}, %s_WORDS}," % (ns, gcount, ln, ", ".join(str(s_) for s_ in outs), name))
     out.append("};")
     out.append("static const int NUM_PROGRAMS = %d;" % len(names))
     out.append("}}  // namespace kb::vmprog")
