@@ -49,7 +49,7 @@ struct kb_ctx {
   // pairing VM (pairing_vm.cu): program + constants resident on the device
   uint64_t* d_vm_prog = nullptr;
   uint32_t* d_vm_consts = nullptr;
-  int vm_slots = 0, vm_gslots = 0;
+  int vm_slots = 0, vm_gslots = 0, vm_block = 128, vm_minb = 2;
   uint64_t vm_out = 0;               // the six output slots, one byte each
 
   // FK open-all cache: hat_s = DFT_2d(reversed SRS prefix) per d

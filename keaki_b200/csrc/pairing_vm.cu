@@ -16,8 +16,7 @@
 
 namespace kb {
 
-static constexpr int VM_BLOCK = 128;   // threads per block = 64 pairings (two lanes each)
-
+template <int VM_BLOCK>   // threads per block = VM_BLOCK / 2 pairings (two lanes each)
 struct DevLane {
   uint4* sm;        // shared slot file ([slot][half][thread]), already offset by threadIdx.x
   uint4* gl;        // global scratch ([gslot][half][thread]), already offset by the global thread index
@@ -67,8 +66,9 @@ struct DevLane {
 
 // mode 0: write the 96 canonical GT words; mode 1: key = BLAKE3-XOF(GT bytes), out = key XOR msg_ct.
 // A warp serves 16 pairings: lane = pairing_in_warp * 2 + t.  MINB = resident blocks per SM the register
-// allocation is held to (the slot budget decides how many fit in shared memory).
-template <int MINB>
+// allocation is held to (the slot budget decides how many fit in shared memory).  The launch shape is chosen so
+// that the batch divides into whole rounds of resident pairings (vm_pick_shape).
+template <int VM_BLOCK, int MINB>
 __global__ void __launch_bounds__(VM_BLOCK, MINB) pairing_vm_kernel(const uint64_t* __restrict__ prog, const uint32_t* __restrict__ consts,
                                                                     uint64_t out_slots, const uint32_t* __restrict__ g1,
                                                                     const uint8_t* __restrict__ g1_inf, const uint32_t* __restrict__ g2,
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(VM_BLOCK, MINB) pairing_vm_kernel(const uint64
   const uint64_t pairing = gtid >> 1;
   const bool live = pairing < n;
   const uint64_t i = live ? pairing : n - 1;   // padding lanes recompute the last pairing (shuffles need all lanes)
-  DevLane ln;
+  DevLane<VM_BLOCK> ln;
   ln.t = threadIdx.x & 1u;
   ln.sm = vm_smem + threadIdx.x;
   ln.gl = scratch + gtid;
@@ -143,18 +143,35 @@ __global__ void __launch_bounds__(VM_BLOCK, MINB) pairing_vm_kernel(const uint64
 // host side
 // ------------------------------------------------------------------------------------------
 // slot file of one block: slots x 2 halves x threads x 16 B
-static int vm_smem_bytes(const kb_ctx* ctx) { return ctx->vm_slots * 2 * VM_BLOCK * 16; }
+static int vm_smem_bytes(const kb_ctx* ctx, int block) { return ctx->vm_slots * 2 * block * 16; }
 
-// Program choice: KB_PAIRING_SLOTS (defaults to the fastest measured variant)
+struct VmShape { int block, minb; };
+// Launch shapes compiled below.  64-thread blocks allow 7 per SM (14 warps: 224 resident pairings), which turns
+// 2^16 pairings on 148 SMs into 1.98 rounds instead of 2.3 rounds of 192.
+static const VmShape VM_SHAPES[] = {{128, 2}, {128, 3}, {128, 4}, {64, 7}};
+
+template <int BLOCK, int MINB>
+static void vm_prepare(const kb_ctx* ctx) {
+  KB_CUDA(cudaFuncSetAttribute(pairing_vm_kernel<BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, vm_smem_bytes(ctx, BLOCK)));
+}
+
+// Program choice: KB_PAIRING_SLOTS / KB_PAIRING_SHAPE="block,minb" (defaults: the fastest measured variant)
 void vm_init(kb_ctx* ctx) {
   using namespace vmprog;
   int slots = 18;
+  ctx->vm_block = 128; ctx->vm_minb = 3;   // 12 warps / SM, 168 registers; measured fastest
   if (const char* e = getenv("KB_PAIRING_SLOTS")) slots = atoi(e);
+  if (const char* e = getenv("KB_PAIRING_SHAPE")) sscanf(e, "%d,%d", &ctx->vm_block, &ctx->vm_minb);
   const Program* pr = nullptr;
   for (int k = 0; k < NUM_PROGRAMS; k++) if (PROGRAMS[k].slots == slots) pr = &PROGRAMS[k];
   if (!pr) throw CudaError("KB_PAIRING_SLOTS names a program variant that was not generated");
+  bool shape_ok = false;
+  for (const VmShape& sh : VM_SHAPES) shape_ok |= sh.block == ctx->vm_block && sh.minb == ctx->vm_minb;
+  if (!shape_ok) throw CudaError("KB_PAIRING_SHAPE names a launch shape that was not compiled");
   ctx->vm_slots = pr->slots;
   ctx->vm_gslots = pr->gslots;
+  if ((vm_smem_bytes(ctx, ctx->vm_block) + 1024) * ctx->vm_minb > 228 * 1024)
+    throw CudaError("pairing VM: slot files of the requested blocks per SM do not fit shared memory");
   ctx->vm_out = 0;
   for (int k = 0; k < 6; k++) ctx->vm_out |= (uint64_t)pr->out[k] << (8 * k);
   const size_t bytes = (size_t)(pr->len + 2) * 8;   // one padding instruction after END (prefetch)
@@ -163,9 +180,7 @@ void vm_init(kb_ctx* ctx) {
   KB_CUDA(cudaMemcpyAsync(ctx->d_vm_prog, pr->words, (size_t)pr->len * 8, cudaMemcpyHostToDevice, ctx->stream));
   KB_CUDA(cudaMalloc((void**)&ctx->d_vm_consts, sizeof(CONSTS)));
   KB_CUDA(cudaMemcpyAsync(ctx->d_vm_consts, CONSTS, sizeof(CONSTS), cudaMemcpyHostToDevice, ctx->stream));
-  KB_CUDA(cudaFuncSetAttribute(pairing_vm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, vm_smem_bytes(ctx)));
-  KB_CUDA(cudaFuncSetAttribute(pairing_vm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, vm_smem_bytes(ctx)));
-  KB_CUDA(cudaFuncSetAttribute(pairing_vm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, vm_smem_bytes(ctx)));
+  vm_prepare<128, 2>(ctx); vm_prepare<128, 3>(ctx); vm_prepare<128, 4>(ctx); vm_prepare<64, 7>(ctx);
 }
 
 void vm_free(kb_ctx* ctx) {
@@ -175,15 +190,17 @@ void vm_free(kb_ctx* ctx) {
 
 static void vm_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
                       uint64_t n, int mode, uint32_t* d_gt_words, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out) {
-  const unsigned blocks = cdiv(2 * n, VM_BLOCK);
-  const uint64_t gstride = (uint64_t)blocks * VM_BLOCK;
+  const int block = ctx->vm_block;
+  const unsigned blocks = cdiv(2 * n, block);
+  const uint64_t gstride = (uint64_t)blocks * block;
   DevBuf<uint4> scratch(ctx, (size_t)(ctx->vm_gslots ? ctx->vm_gslots : 1) * 2 * gstride);
-  int minb = 227 * 1024 / (vm_smem_bytes(ctx) + 1024);   // blocks whose slot files fit one SM
-  if (const char* e = getenv("KB_PAIRING_MINB")) minb = atoi(e);
   timer_start(ctx, KB_T_PAIRING);
-#define KB_VM_GO(MB) KB_LAUNCH(ctx, pairing_vm_kernel<MB>, blocks, VM_BLOCK, vm_smem_bytes(ctx), ctx->d_vm_prog, ctx->d_vm_consts, \
+#define KB_VM_GO(B, MB) KB_LAUNCH(ctx, (pairing_vm_kernel<B, MB>), blocks, B, vm_smem_bytes(ctx, B), ctx->d_vm_prog, ctx->d_vm_consts, \
             ctx->vm_out, d_g1, d_g1_inf, d_g2, d_g2_inf, n, scratch.p, gstride, mode, d_gt_words, d_msg_ct, d_off, d_out)
-  if (minb >= 4) KB_VM_GO(4); else if (minb == 3) KB_VM_GO(3); else KB_VM_GO(2);
+  if (block == 64) KB_VM_GO(64, 7);
+  else if (ctx->vm_minb >= 4) KB_VM_GO(128, 4);
+  else if (ctx->vm_minb == 3) KB_VM_GO(128, 3);
+  else KB_VM_GO(128, 2);
 #undef KB_VM_GO
   timer_stop(ctx, KB_T_PAIRING);
 }

@@ -856,7 +856,7 @@ def limbs(x):
 
 
 # (what, slots): the kernel picks by slot count
-VARIANTS = [("pairing", 14), ("pairing", 18), ("pairing", 28)]
+VARIANTS = [("pairing", 14), ("pairing", 15), ("pairing", 16), ("pairing", 18), ("pairing", 28)]
 
 
 def variant_name(what, ns):
