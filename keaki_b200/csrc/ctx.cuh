@@ -43,6 +43,9 @@ struct kb_ctx {
   uint32_t* d_tau2_tab = nullptr;    // d * 2^(8w) * tau_2
   uint32_t* d_gt_tab = nullptr;      // e(G1, G2)^(d 2^(8w)), Fq12 Montgomery (96 limbs each)
   uint32_t* d_com_tab = nullptr;     // e(com, G2)^(d 2^(8w)) for the cached commitment
+  uint32_t* d_g2_tab16 = nullptr;    // 16-bit-window versions (16 windows x 65535 entries) of the SRS-constant tables
+  uint32_t* d_tau2_tab16 = nullptr;
+  uint32_t* d_gt_tab16 = nullptr;
   uint32_t com_cached[17] = {0};     // xy + inf flag of the commitment the table was built for
   bool com_tab_valid = false;
 

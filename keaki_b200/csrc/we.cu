@@ -6,9 +6,9 @@
 // without changing any output bit (SURVEY.md §8d allows this):
 //   s_i  = e(r_i (C - v_i G1), G2) = A^{r_i} * gT^{-v_i r_i},  A = e(C, G2) (one pairing per
 //          commitment, cached), gT = e(G1, G2);  both are fixed-base GT exponentiations served from
-//          8-bit-window tables (32 windows x 255 entries), i.e. <= 64 Fq12 products per message;
+//          window tables (8-bit windows for A, 16-bit for gT), i.e. <= 48 Fq12 products per message;
 //   ct_i = r_i (tau_2 - a_i G2) = r_i tau_2 - (r_i a_i) G2: two fixed-base G2 multiplications from
-//          8-bit-window affine tables, i.e. <= 64 mixed additions per message.
+//          16-bit-window affine tables, i.e. <= 32 mixed additions per message.
 // GT bytes -> BLAKE3 XOF -> XOR with the message happen in the same kernel; GT never leaves chip.
 #include "ctx.cuh"
 #include "blake3.cuh"
@@ -31,6 +31,13 @@ static constexpr int WE_WIN = 32;          // 8-bit windows over 256 bits
 static constexpr int WE_ENT = 255;         // non-zero digits
 static constexpr size_t G2_TAB_LIMBS = (size_t)WE_WIN * WE_ENT * 32;
 static constexpr size_t GT_TAB_LIMBS = (size_t)WE_WIN * WE_ENT * 96;
+// Bases that are fixed for the life of an SRS (G2, tau_2, gT = e(G1, G2)) get 16-bit windows: 16 x 65535 entries
+// (128 MiB per G2 table, 384 MiB for gT) halve the group operations per message; HBM capacity is what B200 has to
+// spare.  A = e(com, G2) changes per commitment and keeps 8-bit windows (its table is rebuilt per commitment).
+static constexpr int WE_WIN16 = 16;
+static constexpr int WE_ENT16 = 65535;
+static constexpr size_t G2_TAB16_LIMBS = (size_t)WE_WIN16 * WE_ENT16 * 32;
+static constexpr size_t GT_TAB16_LIMBS = (size_t)WE_WIN16 * WE_ENT16 * 96;
 
 __device__ __forceinline__ G1Affine load_g1_flag(const uint32_t* xy, const uint8_t* inf, uint64_t i) {
   if (inf && inf[i]) return G1Affine::infinity();
@@ -67,6 +74,30 @@ __global__ void __launch_bounds__(128) g2_table_fill_kernel(const uint32_t* __re
     if ((d >> bit) & 1u) acc = ec_add(acc, b);
   }
   st_g2(tab + 32 * (size_t)t, to_affine(acc));
+}
+
+// tab16[w][d-1] = d * 2^(16w) * B = tab8[2w+1][d >> 8] + tab8[2w][d & 255], affine
+__global__ void __launch_bounds__(128) g2_table16_kernel(const uint32_t* __restrict__ tab8, uint32_t* __restrict__ tab16) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint32_t)WE_WIN16 * WE_ENT16) return;
+  uint32_t w = t / WE_ENT16, d = t % WE_ENT16 + 1, hi = d >> 8, lo = d & 255u;
+  G2 acc = hi ? to_xyzz(ld_g2(tab8 + 32 * ((size_t)(2 * w + 1) * WE_ENT + hi - 1))) : G2::infinity();
+  if (lo) acc = ec_add_mixed(acc, ld_g2(tab8 + 32 * ((size_t)(2 * w) * WE_ENT + lo - 1)));
+  st_g2(tab16 + 32 * (size_t)t, to_affine(acc));
+}
+// tab16[w][d-1] = base^(d 2^(16w)) = tab8[2w+1][d >> 8] * tab8[2w][d & 255]
+__global__ void __launch_bounds__(128) gt_table16_kernel(const uint32_t* __restrict__ tab8, uint32_t* __restrict__ tab16) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint32_t)WE_WIN16 * WE_ENT16) return;
+  uint32_t w = t / WE_ENT16, d = t % WE_ENT16 + 1, hi = d >> 8, lo = d & 255u;
+  Fq12 acc;
+  if (hi) {
+    acc = ld_fq12(tab8 + 96 * ((size_t)(2 * w + 1) * WE_ENT + hi - 1));
+    if (lo) acc = acc * ld_fq12(tab8 + 96 * ((size_t)(2 * w) * WE_ENT + lo - 1));
+  } else {
+    acc = ld_fq12(tab8 + 96 * ((size_t)(2 * w) * WE_ENT + lo - 1));
+  }
+  st_fq12(tab16 + 96 * (size_t)t, acc);
 }
 
 // bases[w] = A^(2^(8w)), single thread; A must be in GT (cyclotomic)
@@ -107,6 +138,9 @@ static void build_g2_table(kb_ctx* ctx, const uint32_t* d_base_xy, uint32_t* d_t
   KB_LAUNCH(ctx, g2_window_bases_kernel, 1, 32, 0, d_base_xy, bases);
   KB_LAUNCH(ctx, g2_table_fill_kernel, cdiv(WE_WIN * WE_ENT, 128), 128, 0, bases, d_tab);
 }
+static void build_g2_table16(kb_ctx* ctx, const uint32_t* d_tab8, uint32_t* d_tab16) {
+  KB_LAUNCH(ctx, g2_table16_kernel, cdiv((uint64_t)WE_WIN16 * WE_ENT16, 128), 128, 0, d_tab8, d_tab16);
+}
 static void build_gt_table(kb_ctx* ctx, const uint32_t* d_a, uint32_t* d_tab) {
   DevBuf<uint32_t> bases(ctx, WE_WIN * 96);
   KB_LAUNCH(ctx, gt_window_bases_kernel, 1, 32, 0, d_a, bases);
@@ -121,23 +155,34 @@ void we_init_tables(kb_ctx* ctx) {
   DevBuf<uint32_t> g2(ctx, 32), g1(ctx, 16), gt(ctx, 96);
   KB_CUDA(cudaMemcpyAsync(g2, consts::G2_GEN, 128, cudaMemcpyHostToDevice, ctx->stream));
   KB_CUDA(cudaMemcpyAsync(g1, consts::G1_GEN, 64, cudaMemcpyHostToDevice, ctx->stream));
+  KB_CUDA(cudaMalloc((void**)&ctx->d_g2_tab16, G2_TAB16_LIMBS * 4));
+  KB_CUDA(cudaMalloc((void**)&ctx->d_tau2_tab16, G2_TAB16_LIMBS * 4));
+  KB_CUDA(cudaMalloc((void**)&ctx->d_gt_tab16, GT_TAB16_LIMBS * 4));
   build_g2_table(ctx, g2, ctx->d_g2_tab);
+  build_g2_table16(ctx, ctx->d_g2_tab, ctx->d_g2_tab16);
   KB_LAUNCH(ctx, pairing_with_g2gen_kernel, 1, 32, 0, g1, 0u, g2, gt);
   build_gt_table(ctx, gt, ctx->d_gt_tab);
+  KB_LAUNCH(ctx, gt_table16_kernel, cdiv((uint64_t)WE_WIN16 * WE_ENT16, 128), 128, 0, ctx->d_gt_tab, ctx->d_gt_tab16);
   KB_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-void we_set_tau2(kb_ctx* ctx, const uint32_t* d_tau2) { build_g2_table(ctx, d_tau2, ctx->d_tau2_tab); }
+void we_set_tau2(kb_ctx* ctx, const uint32_t* d_tau2) {
+  build_g2_table(ctx, d_tau2, ctx->d_tau2_tab);
+  build_g2_table16(ctx, ctx->d_tau2_tab, ctx->d_tau2_tab16);
+}
 
 void we_free(kb_ctx* ctx) {
   cudaFree(ctx->d_g2_tab); cudaFree(ctx->d_tau2_tab); cudaFree(ctx->d_gt_tab); cudaFree(ctx->d_com_tab);
+  cudaFree(ctx->d_g2_tab16); cudaFree(ctx->d_tau2_tab16); cudaFree(ctx->d_gt_tab16);
   ctx->d_g2_tab = ctx->d_tau2_tab = ctx->d_gt_tab = ctx->d_com_tab = nullptr;
+  ctx->d_g2_tab16 = ctx->d_tau2_tab16 = ctx->d_gt_tab16 = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------
 // encrypt
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t byte_of(const uint32_t* k, int w) { return (k[w >> 2] >> ((w & 3) * 8)) & 255u; }
+__device__ __forceinline__ uint32_t half_of(const uint32_t* k, int w) { return (k[w >> 1] >> ((w & 1) * 16)) & 65535u; }
 
 __global__ void __launch_bounds__(128) encrypt_kernel(const uint32_t* __restrict__ com_tab, const uint32_t* __restrict__ gt_tab,
                                                       const uint32_t* __restrict__ tau2_tab, const uint32_t* __restrict__ g2_tab,
@@ -154,14 +199,16 @@ __global__ void __launch_bounds__(128) encrypt_kernel(const uint32_t* __restrict
   Fr ks = fp_from_mont<FrParams>(-(v * r));      // -v r
   Fr ka = fp_from_mont<FrParams>(r * a);         // r alpha
 
-  // secret = A^r * gT^(-v r)
+  // secret = A^r * gT^(-v r): 8-bit windows for A (per-commitment table), 16-bit windows for gT
   Fq12 s = Fq12::one();
   bool started = false;
   for (int w = 0; w < WE_WIN; w++) {
     uint32_t d = byte_of(kr.v, w);
     if (d) { Fq12 t = ld_fq12(com_tab + 96 * ((size_t)w * WE_ENT + d - 1)); s = started ? s * t : t; started = true; }
-    d = byte_of(ks.v, w);
-    if (d) { Fq12 t = ld_fq12(gt_tab + 96 * ((size_t)w * WE_ENT + d - 1)); s = started ? s * t : t; started = true; }
+  }
+  for (int w = 0; w < WE_WIN16; w++) {
+    uint32_t d = half_of(ks.v, w);
+    if (d) { Fq12 t = ld_fq12(gt_tab + 96 * ((size_t)w * WE_ENT16 + d - 1)); s = started ? s * t : t; started = true; }
   }
   uint32_t words[96];
   gt_to_words(s, words);
@@ -170,11 +217,11 @@ __global__ void __launch_bounds__(128) encrypt_kernel(const uint32_t* __restrict
 
   // ct = r tau_2 - (r alpha) G2
   G2 acc = G2::infinity();
-  for (int w = 0; w < WE_WIN; w++) {
-    uint32_t d = byte_of(kr.v, w);
-    if (d) acc = ec_add_mixed(acc, ld_g2(tau2_tab + 32 * ((size_t)w * WE_ENT + d - 1)));
-    d = byte_of(ka.v, w);
-    if (d) { G2Affine t = ld_g2(g2_tab + 32 * ((size_t)w * WE_ENT + d - 1)); t.y = -t.y; acc = ec_add_mixed(acc, t); }
+  for (int w = 0; w < WE_WIN16; w++) {
+    uint32_t d = half_of(kr.v, w);
+    if (d) acc = ec_add_mixed(acc, ld_g2(tau2_tab + 32 * ((size_t)w * WE_ENT16 + d - 1)));
+    d = half_of(ka.v, w);
+    if (d) { G2Affine t = ld_g2(g2_tab + 32 * ((size_t)w * WE_ENT16 + d - 1)); t.y = -t.y; acc = ec_add_mixed(acc, t); }
   }
   st_g2(ct + 32 * i, to_affine(acc));
   ct_inf[i] = acc.is_inf() ? 1 : 0;
@@ -199,7 +246,7 @@ void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const
   }
   if (!n) return;
   timer_start(ctx, KB_T_ENCRYPT);
-  KB_LAUNCH(ctx, encrypt_kernel, cdiv(n, 128), 128, 0, ctx->d_com_tab, ctx->d_gt_tab, ctx->d_tau2_tab, ctx->d_g2_tab,
+  KB_LAUNCH(ctx, encrypt_kernel, cdiv(n, 128), 128, 0, ctx->d_com_tab, ctx->d_gt_tab16, ctx->d_tau2_tab16, ctx->d_g2_tab16,
             d_points, d_values, d_r, d_msgs, d_off, n, d_ct, d_ct_inf, d_msg_ct);
   timer_stop(ctx, KB_T_ENCRYPT);
 }
