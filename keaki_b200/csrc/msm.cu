@@ -17,22 +17,24 @@
 #include "ctx.cuh"
 #include "msm_digits.cuh"
 #include "consts_gen.cuh"
+#include <cstdlib>
 
 namespace kb {
 
-static constexpr int MSM_SEG = 8;  // buckets per thread in the reduction
 
 // ------------------------------------------------------------------------------------------
 // window choice and table build
 // ------------------------------------------------------------------------------------------
 static int msm_choose_c(uint64_t end) {
+  if (const char* e = getenv("KB_MSM_C")) { int c = atoi(e); if (c >= 4 && c <= 24) return c; }   // tuning override
   if (end <= 256) return 8;
-  if (end <= (1ull << 13)) return 12;
+  if (end <= (1ull << 13)) return 13;   // not 12: 255 = 21 * 12 + 3 would funnel every top digit into 4 buckets
   if (end <= (1ull << 17)) return 16;
   return 20;
 }
 static uint64_t msm_table_cap(int c, uint64_t srs_n) {
-  uint64_t cap = c == 8 ? 256 : c == 12 ? (1ull << 13) : c == 16 ? (1ull << 17) : srs_n;
+  uint64_t cap = c == 8 ? 256 : c == 13 ? (1ull << 13) : c == 16 ? (1ull << 17) : srs_n;
+  if (getenv("KB_MSM_C")) cap = srs_n;
   return cap < srs_n ? cap : srs_n;
 }
 
@@ -139,100 +141,56 @@ __global__ void __launch_bounds__(256) scan_add_kernel(uint32_t* __restrict__ ou
 }
 
 // ------------------------------------------------------------------------------------------
-// bucket reduction: sum_b (b+1) * B_b
+// Load balancing: buckets sorted by population, largest first.  One thread owns one bucket, so a warp runs as
+// long as its fullest bucket; with ~26 +- 5 entries per bucket (and twice that in the buckets the short top
+// window feeds) a warp of arbitrary buckets idles ~30 % of its lanes.  A counting sort of the bucket indices by
+// size gives every warp 32 buckets of (almost) equal length and schedules the long ones first.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) msm_reduce_seg_kernel(const uint32_t* __restrict__ buckets, uint32_t nb,
-                                                             uint32_t* __restrict__ partial) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t lo = t * MSM_SEG;
-  if (lo >= nb) return;
-  uint32_t hi = lo + MSM_SEG < nb ? lo + MSM_SEG : nb;
-  G1 run = G1::infinity(), sum = G1::infinity();
-  for (uint32_t j = hi; j-- > lo;) {
-    run = ec_add(run, ld_g1x(buckets + 32 * (uint64_t)j));
-    sum = ec_add(sum, run);
-  }
-  // sum = sum_j (j - lo + 1) B_j ; add lo * run
-  if (lo != 0 && !run.is_inf()) {
-    G1 m = G1::infinity();
-    for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
-      m = ec_dbl(m);
-      if ((lo >> bit) & 1u) m = ec_add(m, run);
-    }
-    sum = ec_add(sum, m);
-  }
-  st_g1x(partial + 32 * (uint64_t)t, sum);
-}
+static constexpr uint32_t MSM_SIZE_BINS = 1024;   // sizes >= 1023 share the first bin (they are scheduled first anyway)
 
-// tree sum of XYZZ points: each block folds up to 256 * per inputs into one output
-__global__ void __launch_bounds__(256) g1_tree_sum_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t per,
-                                                          uint32_t* __restrict__ out) {
-  __shared__ uint32_t sm[128 * 32];
-  uint64_t base = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * per;
-  G1 acc = G1::infinity();
-  for (uint32_t k = 0; k < per; k++) if (base + k < n) acc = ec_add(acc, ld_g1x(in + 32 * (base + k)));
-  for (int half = 128; half >= 1; half >>= 1) {
-    if (threadIdx.x >= half && threadIdx.x < 2 * half) {
-      uint32_t* s = sm + 32 * (threadIdx.x - half);
-#pragma unroll
-      for (int q = 0; q < 8; q++) { s[q] = acc.x.v[q]; s[8 + q] = acc.y.v[q]; s[16 + q] = acc.zz.v[q]; s[24 + q] = acc.zzz.v[q]; }
-    }
+__global__ void __launch_bounds__(256) msm_size_hist_kernel(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[MSM_SIZE_BINS];
+  for (uint32_t i = threadIdx.x; i < MSM_SIZE_BINS; i += 256) sh[i] = 0;
+  __syncthreads();
+  uint32_t b = blockIdx.x * 256u + threadIdx.x;
+  if (b < nb) {
+    uint32_t sz = offsets[b + 1] - offsets[b];
+    atomicAdd(&sh[MSM_SIZE_BINS - 1 - (sz < MSM_SIZE_BINS - 1 ? sz : MSM_SIZE_BINS - 1)], 1u);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < MSM_SIZE_BINS; i += 256) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// exclusive scan of the 1024 bins in place (one block)
+__global__ void __launch_bounds__(1024) msm_size_scan_kernel(uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[MSM_SIZE_BINS];
+  uint32_t v = hist[threadIdx.x];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (uint32_t o = 1; o < MSM_SIZE_BINS; o <<= 1) {
+    uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
     __syncthreads();
-    if (threadIdx.x < half) {
-      const uint32_t* s = sm + 32 * threadIdx.x;
-      G1 o;
-#pragma unroll
-      for (int q = 0; q < 8; q++) { o.x.v[q] = s[q]; o.y.v[q] = s[8 + q]; o.zz.v[q] = s[16 + q]; o.zzz.v[q] = s[24 + q]; }
-      acc = ec_add(acc, o);
-    }
+    sh[threadIdx.x] += t;
     __syncthreads();
   }
-  if (threadIdx.x == 0) st_g1x(out + 32 * (uint64_t)blockIdx.x, acc);
+  hist[threadIdx.x] = sh[threadIdx.x] - v;
 }
-
-__global__ void g1_finalize_kernel(const uint32_t* __restrict__ xyzz, uint32_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  G1 p = ld_g1x(xyzz);
-  G1Affine a = to_affine(p);
-  st_g1(out_xy, a);
-  if (out_inf) *out_inf = p.is_inf() ? 1 : 0;
-}
-
-__global__ void __launch_bounds__(256) g1_affine_to_xyzz_kernel(const uint32_t* __restrict__ pts, const uint8_t* __restrict__ inf,
-                                                                uint64_t n, uint32_t* __restrict__ out) {
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  G1Affine a = ld_g1(pts + 16 * i);
-  if (inf && inf[i]) a = G1Affine::infinity();
-  st_g1x(out + 32 * i, to_xyzz(a));
-}
-
-// Sums n XYZZ points (array is consumed) and writes the affine result.
-void g1_xyzz_sum_to_affine(kb_ctx* ctx, uint32_t* d_xyzz, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
-  if (n == 0) {
-    KB_CUDA(cudaMemsetAsync(d_out_xy, 0, 64, ctx->stream));
-    if (d_out_inf) KB_CUDA(cudaMemsetAsync(d_out_inf, 1, 1, ctx->stream));
-    return;
+// block-local ranks in shared memory, one global atomic per (block, occupied bin)
+__global__ void __launch_bounds__(256) msm_size_scatter_kernel(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t* __restrict__ cursor,
+                                                               uint32_t* __restrict__ perm) {
+  __shared__ uint32_t sh[MSM_SIZE_BINS];
+  for (uint32_t i = threadIdx.x; i < MSM_SIZE_BINS; i += 256) sh[i] = 0;
+  __syncthreads();
+  uint32_t b = blockIdx.x * 256u + threadIdx.x;
+  uint32_t bin = 0, rank = 0;
+  if (b < nb) {
+    uint32_t sz = offsets[b + 1] - offsets[b];
+    bin = MSM_SIZE_BINS - 1 - (sz < MSM_SIZE_BINS - 1 ? sz : MSM_SIZE_BINS - 1);
+    rank = atomicAdd(&sh[bin], 1u);
   }
-  uint64_t cur_n = n;
-  DevBuf<uint32_t> tmp(ctx, 32 * (size_t)cdiv(n, 256));
-  uint32_t* src = d_xyzz;
-  uint32_t* dst = tmp;
-  while (cur_n > 1) {
-    // keep blocks full when there is a lot to fold, but never fewer than needed
-    uint32_t per = cur_n >= (1u << 16) ? 4 : 1;
-    unsigned blocks = cdiv(cur_n, 256ull * per);
-    KB_LAUNCH(ctx, g1_tree_sum_kernel, blocks, 256, 0, src, cur_n, per, dst);
-    cur_n = blocks;
-    uint32_t* t = src; src = dst; dst = t;
-  }
-  KB_LAUNCH(ctx, g1_finalize_kernel, 1, 32, 0, src, d_out_xy, d_out_inf);
-}
-
-void g1_sum(kb_ctx* ctx, const uint32_t* d_pts, const uint8_t* d_inf, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
-  DevBuf<uint32_t> x(ctx, 32 * (size_t)(n ? n : 1));
-  if (n) KB_LAUNCH(ctx, g1_affine_to_xyzz_kernel, cdiv(n, 256), 256, 0, d_pts, d_inf, n, x);
-  g1_xyzz_sum_to_affine(ctx, x, n, d_out_xy, d_out_inf);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < MSM_SIZE_BINS; i += 256) if (sh[i]) sh[i] = atomicAdd(&cursor[i], sh[i]);
+  __syncthreads();
+  if (b < nb) perm[sh[bin] + rank] = b;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -256,8 +214,6 @@ void msm_g1(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t first, uint64_t n, 
   DevBuf<uint32_t> bsums(ctx, nblk + 1);
   DevBuf<uint32_t> entries(ctx, (size_t)n * tab.nwin);
   DevBuf<uint32_t> buckets(ctx, 32 * (size_t)nb);
-  const uint32_t nseg = cdiv(nb, MSM_SEG);
-  DevBuf<uint32_t> partial(ctx, 32 * (size_t)nseg);
 
   KB_CUDA(cudaMemsetAsync(counts, 0, nb * sizeof(uint32_t), ctx->stream));
   KB_LAUNCH(ctx, msm_count_kernel, cdiv(n, 256), 256, 0, d_scalars, n, c, tab.nwin, counts);
@@ -265,11 +221,16 @@ void msm_g1(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t first, uint64_t n, 
   KB_LAUNCH(ctx, scan_sums_kernel, 1, 32, 0, bsums, nblk);
   KB_LAUNCH(ctx, scan_add_kernel, cdiv(nb + 1, 256), 256, 0, offsets, bsums, cursor, nb, nblk);
   KB_LAUNCH(ctx, msm_scatter_kernel, cdiv(n, 256), 256, 0, d_scalars, n, c, tab.nwin, cursor, entries);
+  DevBuf<uint32_t> size_bins(ctx, MSM_SIZE_BINS);
+  DevBuf<uint32_t> perm(ctx, nb);
+  KB_CUDA(cudaMemsetAsync(size_bins, 0, MSM_SIZE_BINS * sizeof(uint32_t), ctx->stream));
+  KB_LAUNCH(ctx, msm_size_hist_kernel, cdiv(nb, 256), 256, 0, offsets, nb, size_bins);
+  KB_LAUNCH(ctx, msm_size_scan_kernel, 1, MSM_SIZE_BINS, 0, size_bins);
+  KB_LAUNCH(ctx, msm_size_scatter_kernel, cdiv(nb, 256), 256, 0, offsets, nb, size_bins, perm);
   timer_start(ctx, KB_T_MSM_ACC);
-  launch_msm_accumulate(ctx, tab.d, tab.n, first, offsets, entries, nb, buckets);
+  launch_msm_accumulate(ctx, tab.d, tab.n, first, offsets, entries, perm, nb, buckets);
   timer_stop(ctx, KB_T_MSM_ACC);
-  KB_LAUNCH(ctx, msm_reduce_seg_kernel, cdiv(nseg, 128), 128, 0, buckets, nb, partial);
-  g1_xyzz_sum_to_affine(ctx, partial, nseg, d_out_xy, d_out_inf);
+  launch_msm_reduce(ctx, buckets, nb, d_out_xy, d_out_inf);
 }
 
 // ------------------------------------------------------------------------------------------
