@@ -262,23 +262,85 @@ KB_HD Fp<P> fp_from_mont(const Fp<P>& a) {
 template <class P>
 KB_HD Fp<P> fp_to_mont(const Fp<P>& a) { return fp_mul<P>(a, Fp<P>::r2()); }
 
-// a^(p-2) by 4-bit fixed windows (Fermat).  a = 0 -> 0.
+// 256-bit helpers of the inversion below (plain integers, no modular meaning)
+KB_HD void u256_shr1(uint32_t* x) {
+#pragma unroll
+  for (int i = 0; i < 7; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+  x[7] >>= 1;
+}
+KB_HD void u256_shl1(uint32_t* x) {
+#pragma unroll
+  for (int i = 7; i > 0; i--) x[i] = (x[i] << 1) | (x[i - 1] >> 31);
+  x[0] <<= 1;
+}
+KB_HD void u256_add(uint32_t* x, const uint32_t* y) {
+  x[0] = add_cc(x[0], y[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) x[i] = addc_cc(x[i], y[i]);
+  x[7] = addc(x[7], y[7]);
+}
+// x -= y; returns all-ones if the subtraction borrowed (x < y)
+KB_HD uint32_t u256_sub(uint32_t* x, const uint32_t* y) {
+  x[0] = sub_cc(x[0], y[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) x[i] = subc_cc(x[i], y[i]);
+  return subc(0, 0);
+}
+
+// Inverse by Kaliski's binary "almost Montgomery inverse" (shifts, additions and subtractions on the ALU pipe: about a
+// quarter of the issue slots of the Fermat ladder a^(p-2), and none of them on the multiplier pipe).  a = 0 -> 0.
+// Phase 1 keeps u s + v r = p with u = p, v = a, r = 0, s = 1 and ends with v = 0, u = 1, r = -a^-1 2^k (mod p),
+// r < 2p, bitlen(p) <= k <= 2 bitlen(p).  Phase 2 removes 2^k and restores the Montgomery factor: the input is
+// a R, so the wanted a^-1 R equals (a R)^-1 R^2 = x 2^(512 - k) for x = (a R)^-1 2^k.
 template <class P>
 KB_HD_NOINLINE Fp<P> fp_inv(const Fp<P>& a) {
-  Fp<P> tab[16];
-  tab[0] = Fp<P>::one();
-  tab[1] = a;
-  for (int i = 2; i < 16; i++) tab[i] = fp_mul<P>(tab[i - 1], a);
-  Fp<P> r = Fp<P>::one();
-  bool started = false;
-  for (int w = 63; w >= 0; w--) {
-    // exponent p - 2: p's low limb is odd and >= 3 for both fields, so only limb 0 changes
-    uint32_t limb = P::mod(w >> 3) - ((w >> 3) == 0 ? 2u : 0u);
-    uint32_t d = (limb >> ((w & 7) * 4)) & 15u;
-    if (started) { r = fp_sqr<P>(r); r = fp_sqr<P>(r); r = fp_sqr<P>(r); r = fp_sqr<P>(r); }
-    if (d) { r = started ? fp_mul<P>(r, tab[d]) : tab[d]; started = true; }
+  if (a.is_zero()) return a;
+  uint32_t u[8], v[8], r[8], s[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { u[i] = P::mod(i); v[i] = a.v[i]; r[i] = 0; s[i] = 0; }
+  s[0] = 1;
+  uint32_t k = 0;
+  for (;;) {
+    uint32_t vz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) vz |= v[i];
+    if (vz == 0) break;
+    if ((u[0] & 1u) == 0) { u256_shr1(u); u256_shl1(s); }
+    else if ((v[0] & 1u) == 0) { u256_shr1(v); u256_shl1(r); }
+    else {
+      uint32_t d[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) d[i] = v[i];
+      if (u256_sub(d, u) != 0) {          // v < u (both odd, so the difference is even)
+        u256_sub(u, v);
+        u256_shr1(u); u256_add(r, s); u256_shl1(s);
+      } else {                            // v >= u; v = u = 1 at the last step, which ends the loop with v = 0
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = d[i];
+        u256_shr1(v); u256_add(s, r); u256_shl1(r);
+      }
+    }
+    k++;
   }
-  return r;
+  Fp<P> x;
+  {
+    uint32_t t[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = r[i];
+    fp_reduce_once<P>(t);               // r < 2p
+    x.v[0] = sub_cc(P::mod(0), t[0]);    // x = p - r = (a R)^-1 2^k mod p, in [1, p]
+#pragma unroll
+    for (int i = 1; i < 7; i++) x.v[i] = subc_cc(P::mod(i), t[i]);
+    x.v[7] = subc(P::mod(7), t[7]);
+  }
+  // x 2^(512 - k):  k > 256: mont(mont(x, R^2), 2^(512-k));  k <= 256: mont(mont(mont(x, R^2), R^2), 2^(256-k))
+  x = fp_mul<P>(x, Fp<P>::r2());
+  uint32_t e = 512u - k;
+  if (e > 255u) { x = fp_mul<P>(x, Fp<P>::r2()); e -= 256u; }
+  Fp<P> pw = Fp<P>::zero();
+#pragma unroll
+  for (int i = 0; i < 8; i++) pw.v[i] = ((e >> 5) == (uint32_t)i) ? (1u << (e & 31u)) : 0u;
+  return fp_mul<P>(x, pw);
 }
 
 typedef Fp<FqParams> Fq;

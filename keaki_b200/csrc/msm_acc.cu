@@ -47,36 +47,75 @@ void launch_msm_accumulate(kb_ctx* ctx, const uint32_t* tab, uint64_t tab_n, uin
 __device__ __noinline__ G1 g1_add(G1 a, G1 b) { return ec_add(a, b); }
 __device__ __noinline__ G1 g1_dbl(G1 a) { return ec_dbl(a); }
 
-static constexpr int MSM_SEG = 8;  // buckets per thread in the reduction
+// Bucket reduction, two-digit form.  Bucket b (weight b + 1) is written b = hi * C + lo with C = 2^k columns and
+// R = nb / C rows, so that
+//     sum_b (b + 1) B_b = sum_lo (lo + 1) L_lo + sum_hi (hi * C) H_hi,   L_lo = column sums, H_hi = row sums
+// (the running-sum form needs the same two additions per bucket but as 2^(c-1)-long dependent chains; here every
+// addition of the bulk is independent work for the multiplier pipe and only C + R points are left for the weights).
+// Both families of sums are folds of the flat bucket array: rows by adding G consecutive elements, columns by adding
+// G elements n_out apart; each launch runs one fold step of each family.
+struct FoldJob { const uint32_t* in; uint32_t* out; uint32_t n_out, G, sj, si; };   // out[j] = sum_{i<G} in[j * sj + i * si]
 
-// sum_b (b + 1) B_b over segments of MSM_SEG buckets: running sums inside the segment, the segment's weight offset
-// by a short double-and-add, then a tree sum of the segment results and one affine normalisation.
-__global__ void __launch_bounds__(128) msm_reduce_seg_kernel(const uint32_t* __restrict__ buckets, uint32_t nb,
-                                                             uint32_t* __restrict__ partial) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t lo = t * MSM_SEG;
-  if (lo >= nb) return;
-  uint32_t hi = lo + MSM_SEG < nb ? lo + MSM_SEG : nb;
-  G1 run = G1::infinity(), sum = G1::infinity();
-  for (uint32_t j = hi; j-- > lo;) {
-    run = g1_add(run, ld_g1x(buckets + 32 * (uint64_t)j));
-    sum = g1_add(sum, run);
-  }
-  // sum = sum_j (j - lo + 1) B_j ; add lo * run
-  if (lo != 0 && !run.is_inf()) {
-    G1 m = G1::infinity();
-    for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
-      m = g1_dbl(m);
-      if ((lo >> bit) & 1u) m = g1_add(m, run);
+__global__ void __launch_bounds__(128) g1x_fold2_kernel(FoldJob ja, FoldJob jb, uint32_t blocks_a) {
+  const bool second = blockIdx.x >= blocks_a;
+  const FoldJob J = second ? jb : ja;
+  const uint32_t j = (blockIdx.x - (second ? blocks_a : 0u)) * blockDim.x + threadIdx.x;
+  if (j >= J.n_out) return;
+  const uint32_t* p = J.in + 32 * ((uint64_t)j * J.sj);
+  G1 acc = ld_g1x(p);
+  if (J.G > 1) {
+    G1 nxt = ld_g1x(p + 32 * (uint64_t)J.si);
+    for (uint32_t i = 1; i < J.G; i++) {
+      G1 cur = nxt;
+      if (i + 1 < J.G) nxt = ld_g1x(p + 32 * (uint64_t)(i + 1) * J.si);
+      acc = g1_add(acc, cur);
     }
-    sum = g1_add(sum, m);
   }
-  st_g1x(partial + 32 * (uint64_t)t, sum);
+  st_g1x(J.out + 32 * (uint64_t)j, acc);
+}
+
+// weight * P by double-and-add, MSB first
+__device__ __forceinline__ G1 g1_mul_small(const G1& p, uint32_t w) {
+  G1 m = G1::infinity();
+  if (w == 0 || p.is_inf()) return m;
+  for (int bit = 31 - __clz(w); bit >= 0; bit--) {
+    m = g1_dbl(m);
+    if ((w >> bit) & 1u) m = g1_add(m, p);
+  }
+  return m;
+}
+
+// thread t < C: (t + 1) L_t;  C <= t < C + R: ((t - C) * C) H_(t-C);  each block leaves the sum of its 128 terms
+__global__ void __launch_bounds__(128) msm_weigh_kernel(const uint32_t* __restrict__ L, uint32_t C, const uint32_t* __restrict__ H, uint32_t R,
+                                                        uint32_t* __restrict__ out) {
+  __shared__ uint32_t sm[64 * 32];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  G1 acc = G1::infinity();
+  if (t < C) acc = g1_mul_small(ld_g1x(L + 32 * (uint64_t)t), t + 1u);
+  else if (t < C + R) acc = g1_mul_small(ld_g1x(H + 32 * (uint64_t)(t - C)), (t - C) * C);
+  for (int half = 64; half >= 1; half >>= 1) {
+    if (threadIdx.x >= half && threadIdx.x < 2 * half) {
+      uint32_t* s = sm + 32 * (threadIdx.x - half);
+#pragma unroll
+      for (int q = 0; q < 8; q++) { s[q] = acc.x.v[q]; s[8 + q] = acc.y.v[q]; s[16 + q] = acc.zz.v[q]; s[24 + q] = acc.zzz.v[q]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < half) {
+      const uint32_t* s = sm + 32 * threadIdx.x;
+      G1 o;
+#pragma unroll
+      for (int q = 0; q < 8; q++) { o.x.v[q] = s[q]; o.y.v[q] = s[8 + q]; o.zz.v[q] = s[16 + q]; o.zzz.v[q] = s[24 + q]; }
+      acc = g1_add(acc, o);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_g1x(out + 32 * (uint64_t)blockIdx.x, acc);
 }
 
 // tree sum of XYZZ points: each block folds up to 256 * per inputs into one output
+// (with out_xy set, the single block of the last step also writes the affine result)
 __global__ void __launch_bounds__(256) g1_tree_sum_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t per,
-                                                          uint32_t* __restrict__ out) {
+                                                          uint32_t* __restrict__ out, uint32_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf) {
   __shared__ uint32_t sm[128 * 32];
   uint64_t base = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * per;
   G1 acc = G1::infinity();
@@ -97,15 +136,12 @@ __global__ void __launch_bounds__(256) g1_tree_sum_kernel(const uint32_t* __rest
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) st_g1x(out + 32 * (uint64_t)blockIdx.x, acc);
-}
-
-__global__ void g1_finalize_kernel(const uint32_t* __restrict__ xyzz, uint32_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  G1 p = ld_g1x(xyzz);
-  G1Affine a = to_affine(p);
-  st_g1(out_xy, a);
-  if (out_inf) *out_inf = p.is_inf() ? 1 : 0;
+  if (threadIdx.x == 0) {
+    if (out_xy) {
+      st_g1(out_xy, to_affine(acc));
+      if (out_inf) *out_inf = acc.is_inf() ? 1 : 0;
+    } else st_g1x(out + 32 * (uint64_t)blockIdx.x, acc);
+  }
 }
 
 __global__ void __launch_bounds__(256) g1_affine_to_xyzz_kernel(const uint32_t* __restrict__ pts, const uint8_t* __restrict__ inf,
@@ -128,15 +164,16 @@ void g1_xyzz_sum_to_affine(kb_ctx* ctx, uint32_t* d_xyzz, uint64_t n, uint32_t* 
   DevBuf<uint32_t> tmp(ctx, 32 * (size_t)cdiv(n, 256));
   uint32_t* src = d_xyzz;
   uint32_t* dst = tmp;
-  while (cur_n > 1) {
+  for (;;) {
     // keep blocks full when there is a lot to fold, but never fewer than needed
     uint32_t per = cur_n >= (1u << 16) ? 4 : 1;
     unsigned blocks = cdiv(cur_n, 256ull * per);
-    KB_LAUNCH(ctx, g1_tree_sum_kernel, blocks, 256, 0, src, cur_n, per, dst);
+    const bool last = blocks == 1;
+    KB_LAUNCH(ctx, g1_tree_sum_kernel, blocks, 256, 0, src, cur_n, per, dst, last ? d_out_xy : nullptr, d_out_inf);
+    if (last) break;
     cur_n = blocks;
     uint32_t* t = src; src = dst; dst = t;
   }
-  KB_LAUNCH(ctx, g1_finalize_kernel, 1, 32, 0, src, d_out_xy, d_out_inf);
 }
 
 void g1_sum(kb_ctx* ctx, const uint32_t* d_pts, const uint8_t* d_inf, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
@@ -147,10 +184,33 @@ void g1_sum(kb_ctx* ctx, const uint32_t* d_pts, const uint8_t* d_inf, uint64_t n
 
 
 void launch_msm_reduce(kb_ctx* ctx, const uint32_t* buckets, uint32_t nb, uint32_t* d_out_xy, uint8_t* d_out_inf) {
-  const uint32_t nseg = cdiv(nb, MSM_SEG);
-  DevBuf<uint32_t> partial(ctx, 32 * (size_t)nseg);
-  KB_LAUNCH(ctx, msm_reduce_seg_kernel, cdiv(nseg, 128), 128, 0, buckets, nb, partial);
-  g1_xyzz_sum_to_affine(ctx, partial, nseg, d_out_xy, d_out_inf);
+  // nb = 2^(c-1) buckets as R rows of C = 2^k columns, k = ceil((c-1)/2)
+  int lg = 0;
+  while ((1u << lg) < nb) lg++;
+  const uint32_t C = 1u << ((lg + 1) / 2), R = nb / C;
+  DevBuf<uint32_t> bufL(ctx, 32 * (size_t)(nb / 4 + C)), bufH(ctx, 32 * (size_t)(nb / 4 + R));
+  const uint32_t *inL = buckets, *inH = buckets;
+  uint32_t nL = nb, nH = nb;
+  uint32_t *outL = bufL, *outH = bufH;
+  while (nL > C || nH > R) {
+    FoldJob ja = {nullptr, nullptr, 0, 0, 0, 0}, jb = ja;
+    if (nL > C) {   // columns: fold the array onto its first n_out elements (n_out stays a multiple of C)
+      uint32_t G = nL / C < 8 ? nL / C : 8, n_out = nL / G;
+      ja = FoldJob{inL, outL, n_out, G, 1u, n_out};
+      inL = outL; outL += 32 * (size_t)n_out; nL = n_out;
+    }
+    if (nH > R) {   // rows: G consecutive elements (the current row length nH / R is a multiple of G)
+      uint32_t G = nH / R < 8 ? nH / R : 8, n_out = nH / G;
+      jb = FoldJob{inH, outH, n_out, G, G, 1u};
+      inH = outH; outH += 32 * (size_t)n_out; nH = n_out;
+    }
+    const unsigned ba = cdiv(ja.n_out, 128), bb = cdiv(jb.n_out, 128);
+    KB_LAUNCH(ctx, g1x_fold2_kernel, ba + bb, 128, 0, ja, jb, ba);
+  }
+  const unsigned wb = cdiv(C + R, 128);
+  DevBuf<uint32_t> part(ctx, 32 * (size_t)wb);
+  KB_LAUNCH(ctx, msm_weigh_kernel, wb, 128, 0, inL, C, inH, R, part);
+  g1_xyzz_sum_to_affine(ctx, part, wb, d_out_xy, d_out_inf);
 }
 
 }  // namespace kb
