@@ -74,6 +74,34 @@ __global__ void __launch_bounds__(128) g1x_fold2_kernel(FoldJob ja, FoldJob jb, 
   st_g1x(J.out + 32 * (uint64_t)j, acc);
 }
 
+// The same two folds with G adjacent LANES per output (G a power of two <= 32, 32 / G outputs per warp): lane i of a
+// group loads element i and a log2(G)-level shuffle tree adds them.  Used once the arrays are small: the fold is then
+// bound by the length of its dependent chain (log2 G additions against G - 1 in a thread of its own), not by throughput.
+__device__ __forceinline__ G1 g1x_shfl_down(const G1& a, int d, int width) {
+  G1 r;
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    r.x.v[q] = __shfl_down_sync(0xffffffffu, a.x.v[q], d, width);
+    r.y.v[q] = __shfl_down_sync(0xffffffffu, a.y.v[q], d, width);
+    r.zz.v[q] = __shfl_down_sync(0xffffffffu, a.zz.v[q], d, width);
+    r.zzz.v[q] = __shfl_down_sync(0xffffffffu, a.zzz.v[q], d, width);
+  }
+  return r;
+}
+__global__ void __launch_bounds__(128) g1x_fold2_lanes_kernel(FoldJob ja, FoldJob jb, uint32_t blocks_a) {
+  const bool second = blockIdx.x >= blocks_a;
+  const FoldJob J = second ? jb : ja;
+  const uint32_t t = (blockIdx.x - (second ? blocks_a : 0u)) * blockDim.x + threadIdx.x;
+  const uint32_t j = t / J.G, li = t % J.G;
+  const bool live = j < J.n_out;                 // whole groups are live or not; shuffles need every lane
+  G1 acc = live ? ld_g1x(J.in + 32 * ((uint64_t)j * J.sj + (uint64_t)li * J.si)) : G1::infinity();
+  for (int d = (int)J.G >> 1; d >= 1; d >>= 1) {
+    G1 o = g1x_shfl_down(acc, d, (int)J.G);
+    if (li < (uint32_t)d) acc = g1_add(acc, o);
+  }
+  if (live && li == 0) st_g1x(J.out + 32 * (uint64_t)j, acc);
+}
+
 // weight * P by double-and-add, MSB first
 __device__ __forceinline__ G1 g1_mul_small(const G1& p, uint32_t w) {
   G1 m = G1::infinity();
@@ -192,20 +220,29 @@ void launch_msm_reduce(kb_ctx* ctx, const uint32_t* buckets, uint32_t nb, uint32
   const uint32_t *inL = buckets, *inH = buckets;
   uint32_t nL = nb, nH = nb;
   uint32_t *outL = bufL, *outH = bufH;
+  // large arrays: one thread per output, G = 8 (throughput-bound, keeps the multiplier pipe full);
+  // below 2^15 elements: G lanes per output
   while (nL > C || nH > R) {
-    FoldJob ja = {nullptr, nullptr, 0, 0, 0, 0}, jb = ja;
+    const bool lanes = (nL > C ? nL : nH) < (1u << 15);
+    const uint32_t gmax = lanes ? 32u : 8u;
+    FoldJob ja = {nullptr, nullptr, 0, 1, 0, 0}, jb = ja;
     if (nL > C) {   // columns: fold the array onto its first n_out elements (n_out stays a multiple of C)
-      uint32_t G = nL / C < 8 ? nL / C : 8, n_out = nL / G;
+      uint32_t G = nL / C < gmax ? nL / C : gmax, n_out = nL / G;
       ja = FoldJob{inL, outL, n_out, G, 1u, n_out};
       inL = outL; outL += 32 * (size_t)n_out; nL = n_out;
     }
     if (nH > R) {   // rows: G consecutive elements (the current row length nH / R is a multiple of G)
-      uint32_t G = nH / R < 8 ? nH / R : 8, n_out = nH / G;
+      uint32_t G = nH / R < gmax ? nH / R : gmax, n_out = nH / G;
       jb = FoldJob{inH, outH, n_out, G, G, 1u};
       inH = outH; outH += 32 * (size_t)n_out; nH = n_out;
     }
-    const unsigned ba = cdiv(ja.n_out, 128), bb = cdiv(jb.n_out, 128);
-    KB_LAUNCH(ctx, g1x_fold2_kernel, ba + bb, 128, 0, ja, jb, ba);
+    if (!lanes) {
+      const unsigned ba = cdiv(ja.n_out, 128), bb = cdiv(jb.n_out, 128);
+      KB_LAUNCH(ctx, g1x_fold2_kernel, ba + bb, 128, 0, ja, jb, ba);
+    } else {
+      const unsigned ba = cdiv((uint64_t)ja.n_out * ja.G, 128), bb = cdiv((uint64_t)jb.n_out * jb.G, 128);
+      KB_LAUNCH(ctx, g1x_fold2_lanes_kernel, ba + bb, 128, 0, ja, jb, ba);
+    }
   }
   const unsigned wb = cdiv(C + R, 128);
   DevBuf<uint32_t> part(ctx, 32 * (size_t)wb);

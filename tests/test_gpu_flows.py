@@ -249,3 +249,18 @@ def test_full_size_we_roundtrip_65536(ctx):
     tau2 = L.g2_m(bn.g2_mul(bn.G2_GEN, tau))
     ct_o, ci_o, mc_o = co.encrypt_batch(com_xy, com_inf, tau2, P[:m].copy(), V[:m].copy(), rs[:m].copy(), msgs[: 32 * m].copy(), off[: m + 1].copy(), threads=4)
     assert np.array_equal(ct_o, ct[:m]) and np.array_equal(ci_o, ci[:m]) and np.array_equal(mc_o[: 32 * m], mc[: 32 * m])
+
+
+# ------------------------------------------------------------------ BASELINE config 5: laconic OT at scale
+def test_config5_laconic_ot_full_flow_at_scale(ctx):
+    """tests/laconic_ot.rs flow with 2^k - 1 receiver bits on one GPU (k = 16 by default, KB_OT_LOG_N=20 for the
+    BASELINE size): vec_commit with open_fk at d = 2^k, 2 x (2^k - 1) encryptions, 2^k - 1
+    decryptions; all indices round-trip, the other message set does not decrypt, and commitment / proofs /
+    ciphertexts agree with the trapdoor and the C oracle on samples."""
+    from oracle import coracle as co
+    from tests import ot_flow
+    k = int(os.environ.get("KB_OT_LOG_N", "16"))
+    res = ot_flow.run(ctx, k, checker=(bn, co, L))
+    print(json.dumps(res))
+    assert res["roundtrip_all_indices"] and res["other_set_fails"]
+    assert res["commit_vs_trapdoor"] and res["proofs_vs_trapdoor"] and res["ciphertexts_vs_c_oracle"]

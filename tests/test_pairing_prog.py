@@ -63,7 +63,7 @@ def test_constants_match_oracle():
     for k in (1, 2, 3):
         for i in range(6):
             assert gp.CONSTS[gp.C_FROB[k - 1][i]] == bn.f2_pow(bn.XI, i * (bn.Q**k - 1) // 6)
-    assert sum(d << i for i, d in enumerate(gp.Z_NAF)) == bn.Z
+    assert sum(d << i for i, d in enumerate(gp.Z_WNAF)) == bn.Z
 
 
 @pytest.mark.parametrize("slots", [14, 28])

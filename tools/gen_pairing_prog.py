@@ -505,11 +505,14 @@ def miller(t, P, Qx, Qy):
     return f
 
 
-def naf(k):
+def wnaf(k, w):
+    """width-w non-adjacent form, LSB first: non-zero digits are odd, |d| < 2^(w-1)"""
     out = []
     while k:
         if k & 1:
-            d = 2 - (k & 3)
+            d = k % (1 << w)
+            if d >= 1 << (w - 1):
+                d -= 1 << w
             k -= d
         else:
             d = 0
@@ -518,20 +521,29 @@ def naf(k):
     return out
 
 
-Z_NAF = naf(Z)
-assert sum(d << i for i, d in enumerate(Z_NAF)) == Z
+# Exponentiation by z in the cyclotomic subgroup (inverse = conjugate, free): width-4 wNAF of z has 14 non-zero
+# digits in {+-1, +-3, +-5, +-7} against 24 for the plain NAF, so 13 products + 4 for the table (a^2, a^3, a^5, a^7)
+# replace 23; the table lives in slots / the global scratch like every other value.
+Z_WNAF_W = 4
+Z_WNAF = wnaf(Z, Z_WNAF_W)
+assert sum(d << i for i, d in enumerate(Z_WNAF)) == Z and Z_WNAF[-1] == 1
 
 
 def cyclotomic_exp_z(a):
-    ac = f12_conj(a)   # inverse in the cyclotomic subgroup
+    tab = {1: a}
+    top = max(abs(d) for d in Z_WNAF)
+    if top > 1:
+        a2 = cyclotomic_sqr(a)
+        for d in range(3, top + 1, 2):
+            tab[d] = f12_mul(tab[d - 2], a2)
     r = a
-    assert Z_NAF[-1] == 1
-    for i in range(len(Z_NAF) - 2, -1, -1):
+    for i in range(len(Z_WNAF) - 2, -1, -1):
         r = cyclotomic_sqr(r)
-        if Z_NAF[i] == 1:
-            r = f12_mul(r, a)
-        elif Z_NAF[i] == -1:
-            r = f12_mul(r, ac)
+        d = Z_WNAF[i]
+        if d > 0:
+            r = f12_mul(r, tab[d])
+        elif d < 0:
+            r = f12_mul(r, f12_conj(tab[-d]))
     return r
 
 
