@@ -53,6 +53,8 @@ int32_t kb_ctx_create(int32_t device, kb_ctx** out) {
     if (prop.major < 10) throw CudaError(std::string("device ") + prop.name + " is not sm_100-class; this library is built for sm_100a only");
     ctx->sm_count = prop.multiProcessorCount;
     KB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    KB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->ev_copy) KB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     cudaMemPool_t pool;
     KB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thresh = UINT64_MAX;
@@ -84,6 +86,8 @@ void kb_ctx_destroy(kb_ctx* ctx) {
   vm_free(ctx);
   if (ctx->d_srs) cudaFree(ctx->d_srs);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->ev_copy) if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -126,11 +130,11 @@ int32_t kb_msm_g1(kb_ctx* ctx, const uint32_t* scalars, uint64_t first, uint64_t
   need_srs(ctx);
   if (first + n > ctx->srs_n)
     throw ApiError(KB_ERR_POLY_TOO_LARGE, "PolynomialTooLarge(" + std::to_string(first + n) + ", " + std::to_string(ctx->srs_n) + ")");
-  DevIn<uint32_t> s(ctx, scalars, n * 8);
   DevOut<uint32_t> o(ctx, out_xy, 16);
   DevBuf<uint8_t> inf_scratch(ctx, 1);
   DevOut<uint8_t> oi(ctx, out_inf, 1);
-  msm_g1(ctx, s, first, n, o, out_inf ? oi.p : inf_scratch.p);
+  if (n && !is_device_ptr(scalars)) msm_g1_host(ctx, scalars, first, n, o, out_inf ? oi.p : inf_scratch.p);   // copy overlapped with compute
+  else msm_g1(ctx, scalars, first, n, o, out_inf ? oi.p : inf_scratch.p);
   o.finish(); oi.finish();
   KB_API_END(ctx)
 }

@@ -29,6 +29,8 @@ enum { KB_T_TOTAL = 0, KB_T_MSM_ACC = 1, KB_T_PAIRING = 2, KB_T_ENCRYPT = 3, KB_
 struct kb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host-to-device copies that overlap the main stream's kernels (msm_g1_host)
+  cudaEvent_t ev_copy[3] = {};
   std::string err;
   uint64_t launches = 0;
   int sm_count = 148;
@@ -48,6 +50,9 @@ struct kb_ctx {
   uint32_t* d_gt_tab16 = nullptr;
   uint32_t com_cached[17] = {0};     // xy + inf flag of the commitment the table was built for
   bool com_tab_valid = false;
+  uint32_t* d_com_tab16 = nullptr;   // 16-bit-window table of the cached commitment, built once it has served 2^15 messages
+  bool com_tab16_valid = false;
+  uint64_t com_msgs = 0;             // messages encrypted under the cached commitment so far
 
   // pairing VM (pairing_vm.cu): program + constants resident on the device
   uint64_t* d_vm_prog = nullptr;
@@ -162,12 +167,13 @@ __device__ __forceinline__ void st_fq12(uint32_t* p, const Fq12& a) {
 
 // ---- entry points implemented per translation unit (msm.cu, we.cu, poly.cu) ----
 void msm_g1(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t first, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf);
+void msm_g1_host(kb_ctx* ctx, const uint32_t* h_scalars, uint64_t first, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf);
 void g1_sum(kb_ctx* ctx, const uint32_t* d_pts, const uint8_t* d_inf, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf);
 void g1_xyzz_sum_to_affine(kb_ctx* ctx, uint32_t* d_xyzz /* n*32, destroyed */, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf);
 void msm_free_tables(kb_ctx* ctx);
 void g1_mul_gen_batch(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf);
 void launch_msm_accumulate(kb_ctx* ctx, const uint32_t* tab, uint64_t tab_n, uint64_t first, const uint32_t* offsets,
-                           const uint32_t* entries, const uint32_t* perm, uint32_t nb, uint32_t* buckets);
+                           const uint32_t* entries, const uint32_t* perm, uint32_t nb, uint32_t* buckets, bool into);
 void launch_msm_reduce(kb_ctx* ctx, const uint32_t* buckets, uint32_t nb, uint32_t* d_out_xy, uint8_t* d_out_inf);
 void srs_generate(kb_ctx* ctx, const uint32_t* d_tau, uint64_t first_power, uint64_t n, uint32_t* d_tau_g2_out);
 void we_init_tables(kb_ctx* ctx);                       // G2 generator + gT tables (ctx creation)

@@ -196,24 +196,17 @@ __global__ void __launch_bounds__(256) msm_size_scatter_kernel(const uint32_t* _
 // ------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------
-void msm_g1(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t first, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
-  if (n == 0) {
-    KB_CUDA(cudaMemsetAsync(d_out_xy, 0, 64, ctx->stream));
-    if (d_out_inf) KB_CUDA(cudaMemsetAsync(d_out_inf, 1, 1, ctx->stream));
-    return;
-  }
-  if (n > (1ull << 26)) throw ApiError(KB_ERR_ARG, "kb_msm_g1: more than 2^26 points in one call");
-  const int c = msm_choose_c(first + n);
-  const MsmTable& tab = msm_get_table(ctx, c);
+// One pass over a range of points: recode + counting sort of its (point, window) entries by bucket, buckets ordered
+// by population, accumulation.  `into` adds onto the bucket values a previous pass left.
+static void msm_pass(kb_ctx* ctx, const MsmTable& tab, int c, const uint32_t* d_scalars, uint64_t first, uint64_t n,
+                     uint32_t* buckets, bool into) {
   const uint32_t nb = 1u << (c - 1);
   const uint32_t nblk = cdiv(nb, 1024);
-
   DevBuf<uint32_t> counts(ctx, nb);
   DevBuf<uint32_t> offsets(ctx, nb + 1);
   DevBuf<uint32_t> cursor(ctx, nb);
   DevBuf<uint32_t> bsums(ctx, nblk + 1);
   DevBuf<uint32_t> entries(ctx, (size_t)n * tab.nwin);
-  DevBuf<uint32_t> buckets(ctx, 32 * (size_t)nb);
 
   KB_CUDA(cudaMemsetAsync(counts, 0, nb * sizeof(uint32_t), ctx->stream));
   KB_LAUNCH(ctx, msm_count_kernel, cdiv(n, 256), 256, 0, d_scalars, n, c, tab.nwin, counts);
@@ -228,9 +221,59 @@ void msm_g1(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t first, uint64_t n, 
   KB_LAUNCH(ctx, msm_size_scan_kernel, 1, MSM_SIZE_BINS, 0, size_bins);
   KB_LAUNCH(ctx, msm_size_scatter_kernel, cdiv(nb, 256), 256, 0, offsets, nb, size_bins, perm);
   timer_start(ctx, KB_T_MSM_ACC);
-  launch_msm_accumulate(ctx, tab.d, tab.n, first, offsets, entries, perm, nb, buckets);
+  launch_msm_accumulate(ctx, tab.d, tab.n, first, offsets, entries, perm, nb, buckets, into);
   timer_stop(ctx, KB_T_MSM_ACC);
+}
+
+static void msm_empty(kb_ctx* ctx, uint32_t* d_out_xy, uint8_t* d_out_inf) {
+  KB_CUDA(cudaMemsetAsync(d_out_xy, 0, 64, ctx->stream));
+  if (d_out_inf) KB_CUDA(cudaMemsetAsync(d_out_inf, 1, 1, ctx->stream));
+}
+
+void msm_g1(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t first, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
+  if (n == 0) return msm_empty(ctx, d_out_xy, d_out_inf);
+  if (n > (1ull << 26)) throw ApiError(KB_ERR_ARG, "kb_msm_g1: more than 2^26 points in one call");
+  const int c = msm_choose_c(first + n);
+  const MsmTable& tab = msm_get_table(ctx, c);
+  const uint32_t nb = 1u << (c - 1);
+  DevBuf<uint32_t> buckets(ctx, 32 * (size_t)nb);
+  msm_pass(ctx, tab, c, d_scalars, first, n, buckets, false);
   launch_msm_reduce(ctx, buckets, nb, d_out_xy, d_out_inf);
+}
+
+// Scalars in HOST memory (the reference-facing call: `commit` hands over a Vec<Fr>): the host-to-device copy of the
+// scalars is pipelined with the computation.  The first quarter of the points is copied, then sorted and accumulated
+// while the copy engine brings the rest; the second pass adds onto the same buckets (all windows of a point share the
+// one bucket set, so any split of the point range is valid); one bucket reduction at the end.
+void msm_g1_host(kb_ctx* ctx, const uint32_t* h_scalars, uint64_t first, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
+  if (n == 0) return msm_empty(ctx, d_out_xy, d_out_inf);
+  if (n > (1ull << 26)) throw ApiError(KB_ERR_ARG, "kb_msm_g1: more than 2^26 points in one call");
+  DevBuf<uint32_t> sc(ctx, (size_t)n * 8);
+  if (n < (1ull << 18)) {   // small inputs: one copy, one pass
+    KB_CUDA(cudaMemcpyAsync(sc, h_scalars, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return msm_g1(ctx, sc, first, n, d_out_xy, d_out_inf);
+  }
+  const int c = msm_choose_c(first + n);
+  const MsmTable& tab = msm_get_table(ctx, c);
+  const uint32_t nb = 1u << (c - 1);
+  const uint64_t na = n / 4;
+  KB_CUDA(cudaEventRecord(ctx->ev_copy[0], ctx->stream));                     // the scratch allocation is ordered on the main stream
+  KB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[0], 0));
+  KB_CUDA(cudaMemcpyAsync(sc, h_scalars, (size_t)na * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+  KB_CUDA(cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
+  KB_CUDA(cudaMemcpyAsync(sc.p + 8 * na, h_scalars + 8 * na, (size_t)(n - na) * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+  KB_CUDA(cudaEventRecord(ctx->ev_copy[2], ctx->copy_stream));
+  try {
+    DevBuf<uint32_t> buckets(ctx, 32 * (size_t)nb);
+    KB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));
+    msm_pass(ctx, tab, c, sc, first, na, buckets, false);
+    KB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[2], 0));
+    msm_pass(ctx, tab, c, sc.p + 8 * na, first + na, n - na, buckets, true);
+    launch_msm_reduce(ctx, buckets, nb, d_out_xy, d_out_inf);
+  } catch (...) {
+    cudaStreamSynchronize(ctx->copy_stream);   // the scratch buffer must outlive the copies in flight
+    throw;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -10,12 +10,13 @@ namespace kb {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2) msm_accumulate_kernel(const uint32_t* __restrict__ tab, uint64_t tab_n, uint64_t first,
                                                                 const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ entries,
-                                                                const uint32_t* __restrict__ perm, uint32_t nb, uint32_t* __restrict__ buckets) {
+                                                                const uint32_t* __restrict__ perm, uint32_t nb, uint32_t* __restrict__ buckets,
+                                                                int into) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= nb) return;
   const uint32_t b = perm[tid];   // buckets by decreasing population: the 32 lanes of a warp run equally long
   uint32_t lo = offsets[b], hi = offsets[b + 1];
-  G1 acc = G1::infinity();
+  G1 acc = into ? ld_g1x(buckets + 32 * (uint64_t)b) : G1::infinity();   // a second pass continues the first one's sums
   if (lo < hi) {
     uint32_t e = entries[lo];
     G1Affine nxt = ld_g1(tab + 16 * ((uint64_t)((e >> 26) & 31u) * tab_n + first + (e & 0x3ffffffu)));
@@ -34,8 +35,8 @@ __global__ void __launch_bounds__(256, 2) msm_accumulate_kernel(const uint32_t* 
 }
 
 void launch_msm_accumulate(kb_ctx* ctx, const uint32_t* tab, uint64_t tab_n, uint64_t first, const uint32_t* offsets,
-                           const uint32_t* entries, const uint32_t* perm, uint32_t nb, uint32_t* buckets) {
-  KB_LAUNCH(ctx, msm_accumulate_kernel, cdiv(nb, 256), 256, 0, tab, tab_n, first, offsets, entries, perm, nb, buckets);
+                           const uint32_t* entries, const uint32_t* perm, uint32_t nb, uint32_t* buckets, bool into) {
+  KB_LAUNCH(ctx, msm_accumulate_kernel, cdiv(nb, 256), 256, 0, tab, tab_n, first, offsets, entries, perm, nb, buckets, into ? 1 : 0);
 }
 
 

@@ -33,7 +33,10 @@ static constexpr size_t G2_TAB_LIMBS = (size_t)WE_WIN * WE_ENT * 32;
 static constexpr size_t GT_TAB_LIMBS = (size_t)WE_WIN * WE_ENT * 96;
 // Bases that are fixed for the life of an SRS (G2, tau_2, gT = e(G1, G2)) get 16-bit windows: 16 x 65535 entries
 // (128 MiB per G2 table, 384 MiB for gT) halve the group operations per message; HBM capacity is what B200 has to
-// spare.  A = e(com, G2) changes per commitment and keeps 8-bit windows (its table is rebuilt per commitment).
+// spare.  A = e(com, G2) changes per commitment: it starts with 8-bit windows (32 + 8160 Fq12 products to build) and
+// is upgraded to 16-bit windows (one more Fq12 product per entry, ~1 M) once the commitment has served 2^15
+// messages - the point where the 16 products saved per message have paid for the build (laconic OT encrypts
+// 2 n messages under one commitment, tests/laconic_ot.rs:89-109).
 static constexpr int WE_WIN16 = 16;
 static constexpr int WE_ENT16 = 65535;
 static constexpr size_t G2_TAB16_LIMBS = (size_t)WE_WIN16 * WE_ENT16 * 32;
@@ -174,6 +177,8 @@ void we_set_tau2(kb_ctx* ctx, const uint32_t* d_tau2) {
 void we_free(kb_ctx* ctx) {
   cudaFree(ctx->d_g2_tab); cudaFree(ctx->d_tau2_tab); cudaFree(ctx->d_gt_tab); cudaFree(ctx->d_com_tab);
   cudaFree(ctx->d_g2_tab16); cudaFree(ctx->d_tau2_tab16); cudaFree(ctx->d_gt_tab16);
+  if (ctx->d_com_tab16) cudaFree(ctx->d_com_tab16);
+  ctx->d_com_tab16 = nullptr; ctx->com_tab16_valid = false;
   ctx->d_g2_tab = ctx->d_tau2_tab = ctx->d_gt_tab = ctx->d_com_tab = nullptr;
   ctx->d_g2_tab16 = ctx->d_tau2_tab16 = ctx->d_gt_tab16 = nullptr;
 }
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(128) encrypt_kernel(const uint32_t* __restrict
                                                       const uint32_t* __restrict__ tau2_tab, const uint32_t* __restrict__ g2_tab,
                                                       const uint32_t* __restrict__ points, const uint32_t* __restrict__ values,
                                                       const uint32_t* __restrict__ rs, const uint8_t* __restrict__ msgs,
-                                                      const uint64_t* __restrict__ off, uint64_t n,
+                                                      const uint64_t* __restrict__ off, uint64_t n, int com_wide,
                                                       uint32_t* __restrict__ ct, uint8_t* __restrict__ ct_inf, uint8_t* __restrict__ msg_ct) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -199,12 +204,19 @@ __global__ void __launch_bounds__(128) encrypt_kernel(const uint32_t* __restrict
   Fr ks = fp_from_mont<FrParams>(-(v * r));      // -v r
   Fr ka = fp_from_mont<FrParams>(r * a);         // r alpha
 
-  // secret = A^r * gT^(-v r): 8-bit windows for A (per-commitment table), 16-bit windows for gT
+  // secret = A^r * gT^(-v r): 8- or 16-bit windows for A (per-commitment table), 16-bit windows for gT
   Fq12 s = Fq12::one();
   bool started = false;
-  for (int w = 0; w < WE_WIN; w++) {
-    uint32_t d = byte_of(kr.v, w);
-    if (d) { Fq12 t = ld_fq12(com_tab + 96 * ((size_t)w * WE_ENT + d - 1)); s = started ? s * t : t; started = true; }
+  if (com_wide) {
+    for (int w = 0; w < WE_WIN16; w++) {
+      uint32_t d = half_of(kr.v, w);
+      if (d) { Fq12 t = ld_fq12(com_tab + 96 * ((size_t)w * WE_ENT16 + d - 1)); s = started ? s * t : t; started = true; }
+    }
+  } else {
+    for (int w = 0; w < WE_WIN; w++) {
+      uint32_t d = byte_of(kr.v, w);
+      if (d) { Fq12 t = ld_fq12(com_tab + 96 * ((size_t)w * WE_ENT + d - 1)); s = started ? s * t : t; started = true; }
+    }
   }
   for (int w = 0; w < WE_WIN16; w++) {
     uint32_t d = half_of(ks.v, w);
@@ -243,11 +255,20 @@ void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const
     build_gt_table(ctx, a, ctx->d_com_tab);
     memcpy(ctx->com_cached, key, sizeof(key));
     ctx->com_tab_valid = true;
+    ctx->com_tab16_valid = false;
+    ctx->com_msgs = 0;
   }
   if (!n) return;
+  if (!ctx->com_tab16_valid && ctx->com_msgs >= (1ull << 15)) {
+    if (!ctx->d_com_tab16) KB_CUDA(cudaMalloc((void**)&ctx->d_com_tab16, GT_TAB16_LIMBS * 4));
+    KB_LAUNCH(ctx, gt_table16_kernel, cdiv((uint64_t)WE_WIN16 * WE_ENT16, 128), 128, 0, ctx->d_com_tab, ctx->d_com_tab16);
+    ctx->com_tab16_valid = true;
+  }
+  ctx->com_msgs += n;
+  const bool wide = ctx->com_tab16_valid;
   timer_start(ctx, KB_T_ENCRYPT);
-  KB_LAUNCH(ctx, encrypt_kernel, cdiv(n, 128), 128, 0, ctx->d_com_tab, ctx->d_gt_tab16, ctx->d_tau2_tab16, ctx->d_g2_tab16,
-            d_points, d_values, d_r, d_msgs, d_off, n, d_ct, d_ct_inf, d_msg_ct);
+  KB_LAUNCH(ctx, encrypt_kernel, cdiv(n, 128), 128, 0, wide ? ctx->d_com_tab16 : ctx->d_com_tab, ctx->d_gt_tab16, ctx->d_tau2_tab16,
+            ctx->d_g2_tab16, d_points, d_values, d_r, d_msgs, d_off, n, wide ? 1 : 0, d_ct, d_ct_inf, d_msg_ct);
   timer_stop(ctx, KB_T_ENCRYPT);
 }
 

@@ -249,6 +249,9 @@ def test_full_size_we_roundtrip_65536(ctx):
     tau2 = L.g2_m(bn.g2_mul(bn.G2_GEN, tau))
     ct_o, ci_o, mc_o = co.encrypt_batch(com_xy, com_inf, tau2, P[:m].copy(), V[:m].copy(), rs[:m].copy(), msgs[: 32 * m].copy(), off[: m + 1].copy(), threads=4)
     assert np.array_equal(ct_o, ct[:m]) and np.array_equal(ci_o, ci[:m]) and np.array_equal(mc_o[: 32 * m], mc[: 32 * m])
+    # the commitment has now served 2^16 messages: its GT table is upgraded to 16-bit windows (we.cu); same bytes
+    ct2, ci2, mc2 = ctx.encrypt_batch(com_xy, com_inf, P[:4096].copy(), V[:4096].copy(), rs[:4096].copy(), msgs[: 32 * 4096].copy(), off[:4097].copy())
+    assert np.array_equal(ct2, ct[:4096]) and np.array_equal(ci2, ci[:4096]) and np.array_equal(mc2[: 32 * 4096], mc[: 32 * 4096])
 
 
 # ------------------------------------------------------------------ BASELINE config 5: laconic OT at scale
