@@ -118,6 +118,24 @@ int32_t kb_verify_batch(kb_ctx* ctx, const uint32_t* com_xy /* n*16 */, const ui
                         const uint32_t* proofs_xy /* n*16 */, const uint8_t* proofs_inf, uint64_t n,
                         uint8_t* ok /* n */);
 
+/* Wire format: ark-serialize 0.4.2 `CanonicalSerialize` bytes of affine points - what a
+ * `Ciphertext<E>` (src/enc.rs:13, `(E::G2, Vec<u8>)`) and the opening proofs of tests/laconic_ot.rs:60-75 travel in
+ * between sender and receiver (`serialize_compressed` / `serialize_uncompressed` of ark-ec 0.4.2
+ * models/short_weierstrass).  compress != 0: x with the SWFlags in the two top bits of the last byte (G1 32 B,
+ * G2 64 B); compress == 0: x || y (64 / 128 B).  Field elements are 32-byte little-endian canonical integers. */
+int32_t kb_g1_serialize(kb_ctx* ctx, const uint32_t* xy /* n*16 */, const uint8_t* inf /* n or NULL */, uint64_t n,
+                        int32_t compress, uint8_t* out);
+int32_t kb_g2_serialize(kb_ctx* ctx, const uint32_t* xy /* n*32 */, const uint8_t* inf /* n or NULL */, uint64_t n,
+                        int32_t compress, uint8_t* out);
+/* `deserialize_compressed` / `deserialize_uncompressed` (validate != 0: curve equation and, for G2, the r-torsion
+ * subgroup) or their `_unchecked` forms (validate == 0).  ok[i] = 0 where arkworks returns
+ * SerializationError::InvalidData (integer not below q, both flag bits, no square root, failed validation); such
+ * elements come back as infinity. */
+int32_t kb_g1_deserialize(kb_ctx* ctx, const uint8_t* bytes, uint64_t n, int32_t compress, int32_t validate,
+                          uint32_t* xy /* n*16 */, uint8_t* inf /* n */, uint8_t* ok /* n */);
+int32_t kb_g2_deserialize(kb_ctx* ctx, const uint8_t* bytes, uint64_t n, int32_t compress, int32_t validate,
+                          uint32_t* xy /* n*32 */, uint8_t* inf /* n */, uint8_t* ok /* n */);
+
 /* Test hook: elementwise field ops on the device (field: 0 = Fq, 1 = Fr; op: 0 add, 1 sub, 2 mul,
  * 3 neg, 4 inv, 5 from_mont, 6 to_mont, 7 sqr) — lets the GPU tests check the PTX primitives
  * limb-for-limb against the oracle. */

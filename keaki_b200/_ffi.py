@@ -36,6 +36,10 @@ SIGNATURES = {
     "kb_decrypt_batch": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "kb_pairing_batch": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "kb_verify_batch": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "kb_g1_serialize": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "kb_g2_serialize": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "kb_g1_deserialize": (_i32, [_vp, _vp, _u64, _i32, _i32, _vp, _vp, _vp]),
+    "kb_g2_deserialize": (_i32, [_vp, _vp, _u64, _i32, _i32, _vp, _vp, _vp]),
     "kb_debug_fp_op": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _u64]),
     "kb_launch_count": (_u64, [_vp]),
     "kb_last_kernel_ms": (ctypes.c_float, [_vp, _i32]),
@@ -206,6 +210,33 @@ class Context:
         return ok
 
     # ---- diagnostics
+    # ---- wire format (ark-serialize bytes of affine points)
+    def g1_serialize(self, xy, inf=None, compress=True):
+        n = xy.shape[0]
+        out = np.zeros((n, 32 if compress else 64), np.uint8)
+        self._check(self.lib.kb_g1_serialize(self.h, _ptr(xy), _ptr(inf), n, 1 if compress else 0, _ptr(out)))
+        return out
+
+    def g2_serialize(self, xy, inf=None, compress=True):
+        n = xy.shape[0]
+        out = np.zeros((n, 64 if compress else 128), np.uint8)
+        self._check(self.lib.kb_g2_serialize(self.h, _ptr(xy), _ptr(inf), n, 1 if compress else 0, _ptr(out)))
+        return out
+
+    def g1_deserialize(self, data, compress=True, validate=True):
+        data = np.ascontiguousarray(data, np.uint8).reshape(-1, 32 if compress else 64)
+        n = data.shape[0]
+        xy, inf, ok = np.zeros((n, 16), np.uint32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        self._check(self.lib.kb_g1_deserialize(self.h, _ptr(data), n, 1 if compress else 0, 1 if validate else 0, _ptr(xy), _ptr(inf), _ptr(ok)))
+        return xy, inf, ok
+
+    def g2_deserialize(self, data, compress=True, validate=True):
+        data = np.ascontiguousarray(data, np.uint8).reshape(-1, 64 if compress else 128)
+        n = data.shape[0]
+        xy, inf, ok = np.zeros((n, 32), np.uint32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        self._check(self.lib.kb_g2_deserialize(self.h, _ptr(data), n, 1 if compress else 0, 1 if validate else 0, _ptr(xy), _ptr(inf), _ptr(ok)))
+        return xy, inf, ok
+
     def debug_fp_op(self, field, op, a, b):
         out = np.zeros_like(a)
         self._check(self.lib.kb_debug_fp_op(self.h, field, op, _ptr(a), _ptr(b), _ptr(out), a.size // 8))

@@ -63,6 +63,7 @@ int32_t kb_ctx_create(int32_t device, kb_ctx** out) {
     KB_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024));
     for (auto& e : ctx->ev) KB_CUDA(cudaEventCreate(&e));
     we_upload_consts();
+    wire_upload_consts();
     we_init_tables(ctx);
     vm_init(ctx);
     KB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -262,6 +263,52 @@ int32_t kb_verify_batch(kb_ctx* ctx, const uint32_t* com_xy, const uint8_t* com_
   DevOut<uint8_t> o(ctx, ok, n);
   verify_batch(ctx, c, ci, z, v, p, pi, n, o);
   o.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_g1_serialize(kb_ctx* ctx, const uint32_t* xy, const uint8_t* inf, uint64_t n, int32_t compress, uint8_t* out) {
+  KB_API_BEGIN(ctx)
+  need(n == 0 || (xy && out), "kb_g1_serialize: null pointer");
+  DevIn<uint32_t> p(ctx, xy, n * 16);
+  DevIn<uint8_t> pi(ctx, inf, n);
+  DevOut<uint8_t> o(ctx, out, n * (compress ? 32 : 64));
+  g1_serialize(ctx, p, pi, n, compress ? 1 : 0, o);
+  o.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_g2_serialize(kb_ctx* ctx, const uint32_t* xy, const uint8_t* inf, uint64_t n, int32_t compress, uint8_t* out) {
+  KB_API_BEGIN(ctx)
+  need(n == 0 || (xy && out), "kb_g2_serialize: null pointer");
+  DevIn<uint32_t> p(ctx, xy, n * 32);
+  DevIn<uint8_t> pi(ctx, inf, n);
+  DevOut<uint8_t> o(ctx, out, n * (compress ? 64 : 128));
+  g2_serialize(ctx, p, pi, n, compress ? 1 : 0, o);
+  o.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_g1_deserialize(kb_ctx* ctx, const uint8_t* bytes, uint64_t n, int32_t compress, int32_t validate, uint32_t* xy, uint8_t* inf,
+                          uint8_t* ok) {
+  KB_API_BEGIN(ctx)
+  need(n == 0 || (bytes && xy && inf && ok), "kb_g1_deserialize: null pointer");
+  DevIn<uint8_t> b(ctx, bytes, n * (compress ? 32 : 64));
+  DevOut<uint32_t> o(ctx, xy, n * 16);
+  DevOut<uint8_t> oi(ctx, inf, n), ook(ctx, ok, n);
+  g1_deserialize(ctx, b, n, compress ? 1 : 0, validate ? 1 : 0, o, oi, ook);
+  o.finish(); oi.finish(); ook.finish();
+  KB_API_END(ctx)
+}
+
+int32_t kb_g2_deserialize(kb_ctx* ctx, const uint8_t* bytes, uint64_t n, int32_t compress, int32_t validate, uint32_t* xy, uint8_t* inf,
+                          uint8_t* ok) {
+  KB_API_BEGIN(ctx)
+  need(n == 0 || (bytes && xy && inf && ok), "kb_g2_deserialize: null pointer");
+  DevIn<uint8_t> b(ctx, bytes, n * (compress ? 64 : 128));
+  DevOut<uint32_t> o(ctx, xy, n * 32);
+  DevOut<uint8_t> oi(ctx, inf, n), ook(ctx, ok, n);
+  g2_deserialize(ctx, b, n, compress ? 1 : 0, validate ? 1 : 0, o, oi, ook);
+  o.finish(); oi.finish(); ook.finish();
   KB_API_END(ctx)
 }
 

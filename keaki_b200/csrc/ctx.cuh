@@ -196,6 +196,11 @@ void open_batch(kb_ctx* ctx, const uint32_t* d_coeffs, uint64_t d, const uint32_
                 uint32_t* d_proofs, uint8_t* d_inf);
 void open_all_fk(kb_ctx* ctx, const uint32_t* d_coeffs, uint64_t d, uint32_t* d_proofs, uint8_t* d_inf);
 void fk_free(kb_ctx* ctx);
+void wire_upload_consts();
+void g1_serialize(kb_ctx* ctx, const uint32_t* d_xy, const uint8_t* d_inf, uint64_t n, int compress, uint8_t* d_out);
+void g2_serialize(kb_ctx* ctx, const uint32_t* d_xy, const uint8_t* d_inf, uint64_t n, int compress, uint8_t* d_out);
+void g1_deserialize(kb_ctx* ctx, const uint8_t* d_in, uint64_t n, int compress, int validate, uint32_t* d_xy, uint8_t* d_inf, uint8_t* d_ok);
+void g2_deserialize(kb_ctx* ctx, const uint8_t* d_in, uint64_t n, int compress, int validate, uint32_t* d_xy, uint8_t* d_inf, uint8_t* d_ok);
 void debug_fp_op(kb_ctx* ctx, int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, uint64_t n);
 
 }  // namespace kb

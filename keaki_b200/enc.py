@@ -26,3 +26,31 @@ def decrypt(proof: G1, ct, ctx=None) -> bytes:
     out = ctx.decrypt_batch(proof.xy.reshape(1, 16), np.array([proof.inf], np.uint8), key_ct.xy.reshape(1, 32),
                             np.array([key_ct.inf], np.uint8), m, off)
     return bytes(out[:n])
+
+
+# ---- wire format (SURVEY.md §8f.4).  The reference derives no serialisation for `Ciphertext<E>`; as a tuple it would be
+# ark-serialize's `(G2, Vec<u8>)`: the point (compressed 64 B / uncompressed 128 B), then the byte vector as a u64
+# little-endian length followed by the bytes.  The point bytes are produced / parsed on the GPU (kb_g2_serialize).
+def ciphertexts_to_bytes(cts, ctx, compress: bool = True) -> list:
+    """[(G2, bytes)] -> [bytes]"""
+    if not cts:
+        return []
+    xy = np.stack([c[0].xy for c in cts]).astype(np.uint32)
+    inf = np.array([1 if c[0].inf else 0 for c in cts], np.uint8)
+    pts = ctx.g2_serialize(np.ascontiguousarray(xy), inf, compress)
+    return [bytes(pts[i]) + len(c[1]).to_bytes(8, "little") + bytes(c[1]) for i, c in enumerate(cts)]
+
+
+def ciphertexts_from_bytes(blobs, ctx, compress: bool = True, validate: bool = True) -> list:
+    """[bytes] -> [(G2, bytes)]; raises ValueError where arkworks returns SerializationError."""
+    if not blobs:
+        return []
+    plen = 64 if compress else 128
+    for b in blobs:
+        if len(b) < plen + 8 or int.from_bytes(b[plen:plen + 8], "little") != len(b) - plen - 8:
+            raise ValueError("InvalidData: ciphertext length")
+    pts = np.frombuffer(b"".join(bytes(b[:plen]) for b in blobs), np.uint8).reshape(len(blobs), plen)
+    xy, inf, ok = ctx.g2_deserialize(pts, compress, validate)
+    if not ok.all():
+        raise ValueError("InvalidData: ciphertext %d does not decode to a valid G2 point" % int(np.argmin(ok)))
+    return [(G2(xy[i], bool(inf[i])), bytes(b[plen + 8:])) for i, b in enumerate(blobs)]

@@ -455,6 +455,147 @@ def g2_to_bytes(p) -> bytes:
 
 
 # ----------------------------------------------------------------------------------------------
+# ark-serialize 0.4.2 point encodings (`CanonicalSerialize for Affine<P>`, ark-ec 0.4.2
+# models/short_weierstrass/{mod.rs, serialization_flags.rs}) — the wire format a `Ciphertext<E>` (src/enc.rs:13)
+# would travel in.  [restated from memory of the crate; no byte-level vector exists in the
+# reference, so this layer is "parity unpinned" like the rest]
+#   compressed   = x                    with SWFlags in the two top bits of the LAST byte
+#   uncompressed = x || y               with the same flags in the last byte of y
+#   SWFlags: YIsPositive = 0 (y <= -y), PointAtInfinity = 1 << 6, YIsNegative = 1 << 7 (y > -y); infinity is x = y = 0
+#   Fq2 is c0 || c1 and orders by (c1, c0) (`Ord for QuadExtField`); Fq orders by its canonical integer.
+# ----------------------------------------------------------------------------------------------
+SW_FLAG_INFINITY = 0x40
+SW_FLAG_Y_NEGATIVE = 0x80
+
+
+def _fq_is_larger(y):
+    return y > (-y) % Q
+
+
+def _f2_is_larger(y):
+    n = f2_neg(y)
+    return (y[1], y[0]) > (n[1], n[0])
+
+
+def g1_serialize(p, compress: bool) -> bytes:
+    if p is None:
+        out = bytearray(32 if compress else 64)
+        out[-1] |= SW_FLAG_INFINITY
+        return bytes(out)
+    out = bytearray(fq_to_bytes(p[0]) + (b"" if compress else fq_to_bytes(p[1])))
+    if _fq_is_larger(p[1]):
+        out[-1] |= SW_FLAG_Y_NEGATIVE
+    return bytes(out)
+
+
+def g2_serialize(p, compress: bool) -> bytes:
+    if p is None:
+        out = bytearray(64 if compress else 128)
+        out[-1] |= SW_FLAG_INFINITY
+        return bytes(out)
+    out = bytearray(fq_to_bytes(p[0][0]) + fq_to_bytes(p[0][1]) + (b"" if compress else fq_to_bytes(p[1][0]) + fq_to_bytes(p[1][1])))
+    if _f2_is_larger(p[1]):
+        out[-1] |= SW_FLAG_Y_NEGATIVE
+    return bytes(out)
+
+
+def fq_sqrt(a):
+    """q = 3 mod 4: a^((q+1)/4) when a is a square, else None."""
+    a %= Q
+    s = pow(a, (Q + 1) // 4, Q)
+    return s if s * s % Q == a else None
+
+
+def f2_sqrt(a):
+    """a square root in Fq2 = Fq[u]/(u^2+1) by the norm method, or None."""
+    a0, a1 = a[0] % Q, a[1] % Q
+    if a1 == 0:
+        s = fq_sqrt(a0)
+        if s is not None:
+            return (s, 0)
+        return (0, fq_sqrt((-a0) % Q))          # -1 is a non-residue, so -a0 is a square
+    alpha = fq_sqrt((a0 * a0 + a1 * a1) % Q)
+    if alpha is None:
+        return None
+    half = inv_mod(2, Q)
+    c0 = fq_sqrt((a0 + alpha) * half % Q)
+    if c0 is None:
+        c0 = fq_sqrt((a0 - alpha) * half % Q)
+    if c0 is None or c0 == 0:
+        return None
+    c1 = a1 * inv_mod(2 * c0 % Q, Q) % Q
+    r = (c0, c1)
+    return r if f2_sqr(r) == (a0, a1) else None
+
+
+def _read_fq(b):
+    x = int.from_bytes(b, "little")
+    if x >= Q:
+        raise ValueError("InvalidData: field element not below the modulus")
+    return x
+
+
+def _split_flags(b):
+    flags = b[-1] & 0xC0
+    if flags == 0xC0:
+        raise ValueError("InvalidData: both flag bits set")
+    return bytes(b[:-1]) + bytes([b[-1] & 0x3F]), flags
+
+
+def g1_deserialize(b: bytes, compress: bool, validate: bool = True):
+    """`deserialize_{compressed,uncompressed}` (validate) / `_unchecked`; raises ValueError like arkworks errors."""
+    if len(b) != (32 if compress else 64):
+        raise ValueError("InvalidData: length")
+    body, flags = _split_flags(b)
+    x = _read_fq(body[:32])
+    if flags & SW_FLAG_INFINITY:
+        return None
+    if compress:
+        y = fq_sqrt((x * x * x + 3) % Q)
+        if y is None:
+            raise ValueError("InvalidData: x is not on the curve")
+        if _fq_is_larger(y) != bool(flags & SW_FLAG_Y_NEGATIVE):
+            y = (-y) % Q
+    else:
+        y = _read_fq(body[32:64])
+    p = (x, y)
+    if validate and not g1_on_curve(p):
+        raise ValueError("InvalidData: point not on the curve")
+    return p
+
+
+def g2_in_subgroup(p):
+    """[r]P == O without reducing the scalar (g2_mul reduces mod r, which is only valid inside the subgroup)."""
+    acc = None
+    for bit in bin(R)[2:]:
+        acc = g2_add(acc, acc)
+        if bit == '1':
+            acc = g2_add(acc, p)
+    return acc is None
+
+
+def g2_deserialize(b: bytes, compress: bool, validate: bool = True):
+    if len(b) != (64 if compress else 128):
+        raise ValueError("InvalidData: length")
+    body, flags = _split_flags(b)
+    x = (_read_fq(body[:32]), _read_fq(body[32:64]))
+    if flags & SW_FLAG_INFINITY:
+        return None
+    if compress:
+        y = f2_sqrt(f2_add(f2_mul(f2_sqr(x), x), B2))
+        if y is None:
+            raise ValueError("InvalidData: x is not on the curve")
+        if _f2_is_larger(y) != bool(flags & SW_FLAG_Y_NEGATIVE):
+            y = f2_neg(y)
+    else:
+        y = (_read_fq(body[64:96]), _read_fq(body[96:128]))
+    p = (x, y)
+    if validate and not (g2_on_curve(p) and g2_in_subgroup(p)):
+        raise ValueError("InvalidData: point not on the curve / not in the r-torsion subgroup")
+    return p
+
+
+# ----------------------------------------------------------------------------------------------
 # Montgomery-limb helpers (the C ABI carries arkworks' in-RAM representation: x * 2^256 mod m)
 # ----------------------------------------------------------------------------------------------
 def to_mont(x: int, m: int = Q) -> int: return x * MONT_R % m
