@@ -40,6 +40,10 @@ IMAD_PER_ENCRYPT = 38750 * 136       # pairing + 2 G1 smul + 2 G2 smul
 IMAD_PER_DECRYPT = 17000 * 136       # one pairing
 BYTES_PER_MSM_POINT = 96             # 64 B base + 32 B scalar
 BYTES_PER_WE_OP = 544
+# DRAM bytes of one msm_accumulate_kernel launch at 2^20 (dram__bytes_read.sum + dram__bytes_write.sum of the
+# `ncu --set full` capture summarised in profiles/ncu_msm_accumulate_r01_v3.txt): the gathered fixed-base table
+# entries (13 x 2^20 x 64 B) + the entry list + the bucket stores.  Algorithmic bytes are 96 B per point.
+NCU_TRAFFIC_MSM_ACC_2_20 = 1.7662e9 + 6.23e7
 
 
 def load_peaks():
@@ -306,7 +310,8 @@ def run_ours(args):
         "msm_call_device_ms": tot_ms,
         "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": imad_ach / 1e12, "peak": peaks["imad_per_s"] / 1e12, "unit": "TIMAD/s",
                      "frac": imad_ach / peaks["imad_per_s"], "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / tot_ms if tot_ms > 0 else None,
-                     "peak_src": peaks["imad_src"], "traffic": None,
+                     "peak_src": peaks["imad_src"], "traffic": NCU_TRAFFIC_MSM_ACC_2_20 if args.log_msm == 20 else None,
+                     "traffic_unit": "bytes per launch (ncu dram read + write; fixed-base tables are gathered, 13 x 64 B per point)",
                      "note": "algorithmic IMADs = 23,936 per point (reference algorithm: 16 mixed adds x 11 Fq-mul x 136); this kernel executes 13 windows x ~10 Fq-mul x 136",
                      "hbm": {"achieved_gbs": BYTES_PER_MSM_POINT * n_msm / (tot_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"], "peak_src": peaks["src"]}},
         "we": {"metric": "WE encrypt+decrypt ops/s at 2^%d x %d B" % (args.log_we, MSG_LEN), "value": we_value, "unit": "ops/s", "steps": we_steps,
@@ -314,12 +319,13 @@ def run_ours(args):
                "encrypt_per_s": world * n_we / (enc_ms * 1e-3), "decrypt_per_s": world * n_we / (dec_ms * 1e-3),
                "e2e": {"value": we_e2e, "unit": "ops/s", "h2d_bytes_per_step": n_we * (136 + 234), "d2h_bytes_per_step": n_we * (161 + MSG_LEN)},
                "gpu_launches": launches_we,
+               "kernels_ms": {"encrypt_kernel": enc_ms, "pairing_vm_kernel": dec_ms},
                "roofline": {"bound": "imad", "kernel": "pairing_vm_kernel+encrypt_kernel",
                             "achieved": (IMAD_PER_ENCRYPT + IMAD_PER_DECRYPT) * n_we / ((enc_ms + dec_ms) * 1e-3) / 1e12,
                             "peak": peaks["imad_per_s"] / 1e12, "unit": "TIMAD/s",
                             "frac": (IMAD_PER_ENCRYPT + IMAD_PER_DECRYPT) * n_we / ((enc_ms + dec_ms) * 1e-3) / peaks["imad_per_s"],
                             "frac_decrypt": IMAD_PER_DECRYPT * n_we / (dec_ms * 1e-3) / peaks["imad_per_s"],
-                            "note": "algorithmic IMADs as the reference computes (7.58e6 per enc+dec); encrypt here uses fixed-base GT/G2 tables and executes ~7x fewer"}},
+                            "note": "algorithmic IMADs as the reference computes (7.58e6 per enc+dec); encrypt here uses fixed-base GT/G2 tables and executes ~9x fewer, the pairing program executes 15,978 Fq products"}},
         "clocks": clocks, "checks": check, "setup_s": setup_s,
     }
     if cpu is not None:

@@ -94,12 +94,19 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* __rest
   if (i >= n) return;
   int32_t dg[32];
   msm_load_digits(scalars, i, c, nwin, dg);
-  for (int w = 0; w < nwin; w++) {
-    int32_t d = dg[w];
-    if (d == 0) continue;
-    uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
-    uint32_t pos = atomicAdd(&cursor[b], 1u);
-    entries[pos] = (uint32_t)i | ((uint32_t)w << 26) | (d < 0 ? 0x80000000u : 0u);
+  // eight windows at a time: all the cursor atomics of a group are in flight together before their results are used
+  for (int w0 = 0; w0 < nwin; w0 += 8) {
+    uint32_t pos[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      int32_t d = w0 + k < nwin ? dg[w0 + k] : 0;
+      pos[k] = d != 0 ? atomicAdd(&cursor[(uint32_t)(d < 0 ? -d : d) - 1u], 1u) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      int32_t d = w0 + k < nwin ? dg[w0 + k] : 0;
+      if (d != 0) entries[pos[k]] = (uint32_t)i | ((uint32_t)(w0 + k) << 26) | (d < 0 ? 0x80000000u : 0u);
+    }
   }
 }
 

@@ -73,6 +73,11 @@ def main():
         "gt_5_7": bn.gt_to_bytes(gt).hex(),
         "gt_one_key32": kr.gt_key(bn.F12_ONE, 32).hex(),
         "tau_g2": [[str(setup.tau_g2[0][0]), str(setup.tau_g2[0][1])], [str(setup.tau_g2[1][0]), str(setup.tau_g2[1][1])]],
+        # wire format: ark-serialize bytes of the proofs (G1) and of the ciphertext points (G2)
+        "wire": {"proofs_compressed": [bn.g1_serialize(q, True).hex() for q in proofs],
+                 "proofs_uncompressed": [bn.g1_serialize(q, False).hex() for q in proofs],
+                 "ct_compressed": [bn.g2_serialize(c[0], True).hex() for c in cts],
+                 "ct_uncompressed": [bn.g2_serialize(c[0], False).hex() for c in cts]},
     }
     json.dump(vec, open(os.path.join(HERE, "oracle_vectors.json"), "w"), indent=1)
     print("golden fixtures written to", HERE)

@@ -152,6 +152,14 @@ def test_golden_vectors_on_gpu(ctx):
     assert [k.hex() for k in keys] == v["keys32"]
     gt = ctx.pairing_batch(L.g1_m(bn.g1_mul(bn.G1_GEN, 5)).reshape(1, 16), None, L.g2_m(bn.g2_mul(bn.G2_GEN, 7)).reshape(1, 32), None)
     assert bytes(gt[0]).hex() == v["gt_5_7"]
+    # wire bytes of the proofs and ciphertext points
+    pxy = np.stack([q.xy for q in proofs]); pinf = np.array([q.inf for q in proofs], np.uint8)
+    cxy = np.stack([c[0].xy for c in cts]); cinf = np.array([c[0].inf for c in cts], np.uint8)
+    for compress, kp, kc in ((True, "proofs_compressed", "ct_compressed"), (False, "proofs_uncompressed", "ct_uncompressed")):
+        assert [bytes(b).hex() for b in ctx.g1_serialize(pxy, pinf, compress)] == v["wire"][kp]
+        assert [bytes(b).hex() for b in ctx.g2_serialize(cxy, cinf, compress)] == v["wire"][kc]
+        back, binf, ok = ctx.g2_deserialize(np.frombuffer(bytes.fromhex("".join(v["wire"][kc])), np.uint8), compress, True)
+        assert ok.all() and np.array_equal(back, cxy) and np.array_equal(binf, cinf)
 
 
 # ------------------------------------------------------------------ BASELINE config 3: vec open-all at 2^12

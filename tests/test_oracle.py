@@ -85,3 +85,6 @@ def test_golden_vectors_reproduce():
     assert kr.vec_decrypt(proofs, cts) == msgs
     assert bn.gt_to_bytes(bn.pairing(bn.g1_mul(bn.G1_GEN, 5), bn.g2_mul(bn.G2_GEN, 7))).hex() == v["gt_5_7"]
     assert v["gt_one_key32"] == "207d2aaa3257b30b7c371b6804480c9b2a7a04b4f69847270c5aadf5e5bc9454"
+    assert [bn.g1_serialize(q, True).hex() for q in proofs] == v["wire"]["proofs_compressed"]
+    assert [bn.g2_serialize(c[0], False).hex() for c in cts] == v["wire"]["ct_uncompressed"]
+    assert [bn.g2_deserialize(bytes.fromhex(h), True) for h in v["wire"]["ct_compressed"]] == [c[0] for c in cts]
