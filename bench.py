@@ -336,6 +336,15 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """Host cores this process may use.  torchrun exports OMP_NUM_THREADS=1, so the OpenMP default is not the answer: the
+    CPU arm runs on rank 0 alone and takes every core of its affinity mask."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def make_cpu_inputs(n_msm, n_we, tau):
     """Inputs for the CPU arm: bases k_i*G1 with cheap-to-make k_i (timing does not depend on the values)."""
     from oracle import bn254 as bn
@@ -377,8 +386,7 @@ def cpu_time_we(n, tau, threads, rng):
 
 def cpu_baseline(args, tau):
     """C restatement of the reference CPU path (oracle/c) timed on this box's host cores, bounded sample."""
-    from oracle import coracle as co
-    cores = co.max_threads()
+    cores = host_threads()
     n = 1 << min(args.log_msm, 18)
     bases, scalars, rng = make_cpu_inputs(n, 0, tau)
     t_all = cpu_time_msm(bases, scalars, cores)
@@ -402,8 +410,7 @@ def run_reference(args):
     world, rank, _ = dist_setup(args.gpus)
     if rank != 0:
         return
-    from oracle import coracle as co
-    cores = co.max_threads()
+    cores = host_threads()
     from oracle import bn254 as _bn
     tau = 0x1D2C3B4A5968778695A4B3C2D1E0F1E2D3C4B5A69788796A5B4C3D2E1F001122 % _bn.R
     n = 1 << min(args.log_msm, 18)

@@ -141,6 +141,135 @@ __global__ void __launch_bounds__(128) msm_weigh_kernel(const uint32_t* __restri
   if (threadIdx.x == 0) st_g1x(out + 32 * (uint64_t)blockIdx.x, acc);
 }
 
+// ------------------------------------------------------------------------------------------
+// Quad-cooperative group law for the dependent tails of the reduction.  Once only a few thousand points are left the
+// reduction is a chain of ~45 dependent group operations, and a lone warp needs ~0.43 us per field product however few
+// of its lanes are busy.  Four adjacent lanes (a quad) therefore share one group operation: all four hold the same
+// operands, each computes ONE of the independent products of a level of the formula, and the products are exchanged
+// inside the quad by shuffles (quad-wide masks: quads of a warp may diverge from one another).  An addition is 4
+// product levels instead of 14 products in sequence, a doubling 3 instead of 9.
+// ------------------------------------------------------------------------------------------
+struct QuadLane { uint32_t q, mask; };   // lane index inside the quad, shuffle mask of the quad
+__device__ __forceinline__ QuadLane quad_lane() {
+  QuadLane ql;
+  const uint32_t lane = threadIdx.x & 31u;
+  ql.q = lane & 3u;
+  ql.mask = 0xFu << (lane & 28u);
+  return ql;
+}
+__device__ __forceinline__ Fq quad_get(const Fq& v, int src, const QuadLane& ql) {   // v as held by lane `src` of the quad
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(ql.mask, v.v[i], src, 4);
+  return r;
+}
+__device__ __forceinline__ Fq sel4(uint32_t q, const Fq& a0, const Fq& a1, const Fq& a2, const Fq& a3) {
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = q == 0 ? a0.v[i] : q == 1 ? a1.v[i] : q == 2 ? a2.v[i] : a3.v[i];
+  return r;
+}
+__device__ __noinline__ Fq quad_mul(Fq a, Fq b) { return fp_mul_inl<FqParams>(a, b); }
+
+// add-2008-s over a quad; p and q (and the result) are replicated in the four lanes
+__device__ __noinline__ G1 g1_add4(G1 p, G1 q, QuadLane ql) {
+  Fq m = quad_mul(sel4(ql.q, p.x, q.x, p.y, q.y), sel4(ql.q, q.zz, p.zz, q.zzz, p.zzz));
+  const Fq u1 = quad_get(m, 0, ql), u2 = quad_get(m, 1, ql), s1 = quad_get(m, 2, ql), s2 = quad_get(m, 3, ql);
+  const Fq pp_ = u2 - u1, r_ = s2 - s1;
+  m = quad_mul(sel4(ql.q, pp_, r_, p.zz, p.zzz), sel4(ql.q, pp_, r_, q.zz, q.zzz));
+  const Fq pp = quad_get(m, 0, ql), rr = quad_get(m, 1, ql), zz12 = quad_get(m, 2, ql), zzz12 = quad_get(m, 3, ql);
+  m = quad_mul(sel4(ql.q, pp_, u1, zz12, pp_), pp);
+  const Fq ppp = quad_get(m, 0, ql), qv = quad_get(m, 1, ql), zz3 = quad_get(m, 2, ql);
+  G1 r;
+  r.x = rr - ppp - dbl(qv);
+  m = quad_mul(sel4(ql.q, r_, s1, zzz12, r_), sel4(ql.q, qv - r.x, ppp, ppp, ppp));
+  r.y = quad_get(m, 0, ql) - quad_get(m, 1, ql);
+  r.zz = zz3;
+  r.zzz = quad_get(m, 2, ql);
+  // exceptional cases: every lane decides alike (replicated operands); no shuffles below this line
+  if (q.is_inf()) return p;
+  if (p.is_inf()) return q;
+  if (pp_.is_zero()) return r_.is_zero() ? g1_dbl(p) : G1::infinity();
+  return r;
+}
+// dbl-2008-s-1 over a quad
+__device__ __noinline__ G1 g1_dbl4(G1 p, QuadLane ql) {
+  const Fq u = dbl(p.y);
+  Fq m = quad_mul(sel4(ql.q, u, p.x, u, p.x), sel4(ql.q, u, p.x, u, p.x));
+  const Fq v = quad_get(m, 0, ql), xx = quad_get(m, 1, ql);
+  const Fq mm_ = dbl(xx) + xx;
+  m = quad_mul(sel4(ql.q, u, p.x, mm_, v), sel4(ql.q, v, v, mm_, p.zz));
+  const Fq w = quad_get(m, 0, ql), sv = quad_get(m, 1, ql), msq = quad_get(m, 2, ql), zz3 = quad_get(m, 3, ql);
+  G1 r;
+  r.x = msq - dbl(sv);
+  m = quad_mul(sel4(ql.q, mm_, w, w, w), sel4(ql.q, sv - r.x, p.y, p.zzz, p.y));
+  r.y = quad_get(m, 0, ql) - quad_get(m, 1, ql);
+  r.zz = zz3;
+  r.zzz = quad_get(m, 2, ql);
+  if (p.is_inf()) return p;
+  return r;
+}
+
+__device__ __forceinline__ void g1x_to_smem(uint32_t* s, const G1& a) {
+#pragma unroll
+  for (int q = 0; q < 8; q++) { s[q] = a.x.v[q]; s[8 + q] = a.y.v[q]; s[16 + q] = a.zz.v[q]; s[24 + q] = a.zzz.v[q]; }
+}
+__device__ __forceinline__ G1 g1x_from_smem(const uint32_t* s) {
+  G1 o;
+#pragma unroll
+  for (int q = 0; q < 8; q++) { o.x.v[q] = s[q]; o.y.v[q] = s[8 + q]; o.zz.v[q] = s[16 + q]; o.zzz.v[q] = s[24 + q]; }
+  return o;
+}
+// sum over the NQ quads of a block (acc replicated per quad); the result is valid in quad 0
+template <int NQ>
+__device__ __forceinline__ G1 quad_block_sum(G1 acc, const QuadLane& ql, uint32_t* sm /* NQ/2 * 32 words */) {
+  const int qi = threadIdx.x >> 2;
+  for (int half = NQ / 2; half >= 1; half >>= 1) {
+    if (qi >= half && qi < 2 * half && ql.q == 0) g1x_to_smem(sm + 32 * (qi - half), acc);
+    __syncthreads();
+    if (qi < half) acc = g1_add4(acc, g1x_from_smem(sm + 32 * qi), ql);
+    __syncthreads();
+  }
+  return acc;
+}
+
+// quad j < C: (j + 1) L_j;  C <= j < C + R: ((j - C) * C) H_(j-C), double-and-add over the quad; each block of 32 quads
+// leaves the sum of its terms
+__global__ void __launch_bounds__(128) msm_weigh4_kernel(const uint32_t* __restrict__ L, uint32_t C, const uint32_t* __restrict__ H, uint32_t R,
+                                                         uint32_t* __restrict__ out) {
+  __shared__ uint32_t sm[16 * 32];
+  const QuadLane ql = quad_lane();
+  const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  G1 p = G1::infinity();
+  uint32_t w = 0;
+  if (j < C) { p = ld_g1x(L + 32 * (uint64_t)j); w = j + 1u; }
+  else if (j < C + R) { p = ld_g1x(H + 32 * (uint64_t)(j - C)); w = (j - C) * C; }
+  G1 acc = G1::infinity();
+  if (w != 0 && !p.is_inf()) {
+    acc = p;
+    for (int bit = 30 - __clz(w); bit >= 0; bit--) {
+      acc = g1_dbl4(acc, ql);
+      if ((w >> bit) & 1u) acc = g1_add4(acc, p, ql);
+    }
+  }
+  acc = quad_block_sum<32>(acc, ql, sm);
+  if (threadIdx.x == 0) st_g1x(out + 32 * (uint64_t)blockIdx.x, acc);
+}
+
+// sum of n <= 64 points by one block of 64 quads, affine result
+__global__ void __launch_bounds__(256) g1_sum4_final_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out_xy,
+                                                            uint8_t* __restrict__ out_inf) {
+  __shared__ uint32_t sm[32 * 32];
+  const QuadLane ql = quad_lane();
+  const uint32_t qi = threadIdx.x >> 2;
+  G1 acc = qi < n ? ld_g1x(in + 32 * (uint64_t)qi) : G1::infinity();
+  acc = quad_block_sum<64>(acc, ql, sm);
+  if (threadIdx.x == 0) {
+    st_g1(out_xy, to_affine(acc));
+    if (out_inf) *out_inf = acc.is_inf() ? 1 : 0;
+  }
+}
+
 // tree sum of XYZZ points: each block folds up to 256 * per inputs into one output
 // (with out_xy set, the single block of the last step also writes the affine result)
 __global__ void __launch_bounds__(256) g1_tree_sum_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t per,
@@ -246,7 +375,12 @@ void launch_msm_reduce(kb_ctx* ctx, const uint32_t* buckets, uint32_t nb, uint32
     }
   }
   const unsigned wb = cdiv(C + R, 128);
-  DevBuf<uint32_t> part(ctx, 32 * (size_t)wb);
+  DevBuf<uint32_t> part(ctx, 32 * (size_t)(wb > 64 ? wb : 64));
+  if (const unsigned wb4 = cdiv(4ull * (C + R), 128); wb4 <= 64) {   // quad-cooperative tail
+    KB_LAUNCH(ctx, msm_weigh4_kernel, wb4, 128, 0, inL, C, inH, R, part);
+    KB_LAUNCH(ctx, g1_sum4_final_kernel, 1, 256, 0, part, wb4, d_out_xy, d_out_inf);
+    return;
+  }
   KB_LAUNCH(ctx, msm_weigh_kernel, wb, 128, 0, inL, C, inH, R, part);
   g1_xyzz_sum_to_affine(ctx, part, wb, d_out_xy, d_out_inf);
 }
