@@ -66,8 +66,14 @@ static void f_sub(const field_t* F, fe* r, const fe* a, const fe* b) {
 }
 static void f_neg(const field_t* F, fe* r, const fe* a) { fe z = {{0, 0, 0, 0}}; f_sub(F, r, &z, a); }
 static void f_dbl(const field_t* F, fe* r, const fe* a) { f_add(F, r, a, a); }
+/* Instrumentation ("exact counts from an instrumented oracle"): field products executed since the last
+ * reset, counted only while enabled and only meaningful for threads = 1 calls. */
+static int ko_cnt_on = 0;
+static uint64_t ko_cnt = 0;
+uint64_t ko_count_muls(int enable) { uint64_t c = ko_cnt; ko_cnt = 0; ko_cnt_on = enable; return c; }
 /* CIOS Montgomery product */
 static void f_mul(const field_t* F, fe* r, const fe* a, const fe* b) {
+  if (ko_cnt_on) ko_cnt++;
   uint64_t t[6] = {0, 0, 0, 0, 0, 0};
   for (int i = 0; i < 4; i++) {
     u128 c = 0;

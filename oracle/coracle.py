@@ -32,6 +32,14 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+def count_muls(enable: bool) -> int:
+    """Field products (Fq and Fr, Montgomery) executed by single-thread calls since the last call of this function;
+    `enable` switches the counter for what follows.  Instrumentation for the per-unit work figures in DESIGN.md."""
+    lib = load()
+    lib.ko_count_muls.restype = ctypes.c_uint64
+    return int(lib.ko_count_muls(1 if enable else 0))
+
+
 def max_threads():
     return int(load().ko_max_threads())
 

@@ -169,3 +169,17 @@ def test_signed_digits(c):
         he.he_msm_digits(P(L.int_to_limbs(k)), c, nwin, d)
         assert sum(int(d[w]) << (c * w) for w in range(nwin)) == k
         assert all(-(1 << (c - 1)) < int(x) <= (1 << (c - 1)) for x in d)
+
+
+def test_binary_inversion_edge_representations():
+    """fp_inv is Kaliski's almost-inverse + a power-of-two fix-up that branches on k <= 256 (fp.cuh): exercise Montgomery
+    images at the extremes of the iteration count (1, 2, small, p - 1, powers of two) for both fields."""
+    for field, mod in ((0, bn.Q), (1, bn.R)):
+        rinv = pow(1 << 256, -1, mod)
+        images = [1, 2, 3, 4, 5, mod - 1, mod - 2, 1 << 253, (1 << 253) + 1, (mod - 1) // 2, (mod + 1) // 2, 1 << 128, (1 << 200) - 1]
+        for am in images:
+            a = am * rinv % mod
+            A = L.int_to_limbs(am)
+            out = np.zeros(8, np.uint32)
+            he.he_fp_op(field, 4, P(A), P(A), P(out), 1)
+            assert bn.from_mont(L.limbs_to_int(out), mod) == pow(a, -1, mod), (field, am)

@@ -81,3 +81,19 @@ def test_encrypt_decrypt_match_python_oracle():
         assert bytes(out[int(off[i]): int(off[i + 1])]) == ref[i]
         if i != 1:
             assert ref[i] == msgs[i]
+
+
+def test_product_counter_counts_single_thread_work():
+    """The instrumentation behind DESIGN.md's exact per-unit work table: counts are deterministic and scale with n."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    pts = [bn.g1_mul(bn.G1_GEN, k) for k in (1, 2, 3, 5)]
+    bases = np.tile(L.g1_vec(pts).reshape(4, 16), (64, 1))
+    sc = rng.integers(0, 1 << 32, size=(256, 8), dtype=np.uint64).astype(np.uint32); sc[:, 7] &= 0x0FFFFFFF
+    co.count_muls(True)
+    co.msm_g1(bases, sc, threads=1)
+    c1 = co.count_muls(True)
+    co.msm_g1(bases, sc, threads=1)
+    c2 = co.count_muls(False)
+    co.msm_g1(bases, sc, threads=1)
+    assert c1 == c2 > 256 * 50 and co.count_muls(False) == 0
