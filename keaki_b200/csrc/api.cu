@@ -2,6 +2,7 @@
 // host buffers, stream synchronisation and error translation.  There is no host arithmetic and no
 // CPU fallback anywhere behind these entry points.
 #include "ctx.cuh"
+#include <cstdlib>
 
 using namespace kb;
 
@@ -53,7 +54,13 @@ int32_t kb_ctx_create(int32_t device, kb_ctx** out) {
     if (prop.major < 10) throw CudaError(std::string("device ") + prop.name + " is not sm_100-class; this library is built for sm_100a only");
     ctx->sm_count = prop.multiProcessorCount;
     KB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    KB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    {
+      int prio_lo = 0, prio_hi = 0;   // the side stream (copies, second-pass sort) gets the higher priority
+      KB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      int prio = prio_hi;
+      if (const char* e = getenv("KB_SIDE_PRIO")) prio = atoi(e) > 0 ? prio_lo : atoi(e) < 0 ? prio_hi : 0;   // tuning override
+      KB_CUDA(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio));
+    }
     for (auto& e : ctx->ev_copy) KB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     cudaMemPool_t pool;
     KB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));

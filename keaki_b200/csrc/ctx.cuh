@@ -30,7 +30,7 @@ struct kb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // host-to-device copies that overlap the main stream's kernels (msm_g1_host)
-  cudaEvent_t ev_copy[3] = {};
+  cudaEvent_t ev_copy[4] = {};
   std::string err;
   uint64_t launches = 0;
   int sm_count = 148;

@@ -203,33 +203,34 @@ __global__ void __launch_bounds__(256) msm_size_scatter_kernel(const uint32_t* _
 // ------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------
-// One pass over a range of points: recode + counting sort of its (point, window) entries by bucket, buckets ordered
-// by population, accumulation.  `into` adds onto the bucket values a previous pass left.
-static void msm_pass(kb_ctx* ctx, const MsmTable& tab, int c, const uint32_t* d_scalars, uint64_t first, uint64_t n,
-                     uint32_t* buckets, bool into) {
+// One pass over a range of points = sort (recode + counting sort of its (point, window) entries by bucket, buckets
+// ordered by population) + accumulation.  The sort is bound by L2 atomics and scattered stores, the accumulation by the
+// multiplier pipe, so the sort of the NEXT pass runs on a side stream underneath the accumulation of the current one.
+struct MsmSort {
+  DevBuf<uint32_t> counts, offsets, cursor, bsums, entries, size_bins, perm;
+  uint64_t n;
+  MsmSort(kb_ctx* ctx, uint32_t nb, uint64_t n_, int nwin)
+      : counts(ctx, nb), offsets(ctx, nb + 1), cursor(ctx, nb), bsums(ctx, cdiv(nb, 1024) + 1), entries(ctx, (size_t)n_ * nwin),
+        size_bins(ctx, MSM_SIZE_BINS), perm(ctx, nb), n(n_) {}
+};
+#define KB_LAUNCH_ON(ctx, st, kernel, grid, block, smem, ...) do { \
+  kernel<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__); \
+  (ctx)->launches++; KB_CUDA(cudaGetLastError()); } while (0)
+
+static void msm_sort(kb_ctx* ctx, cudaStream_t st, MsmSort& w, const MsmTable& tab, int c, const uint32_t* d_scalars) {
   const uint32_t nb = 1u << (c - 1);
   const uint32_t nblk = cdiv(nb, 1024);
-  DevBuf<uint32_t> counts(ctx, nb);
-  DevBuf<uint32_t> offsets(ctx, nb + 1);
-  DevBuf<uint32_t> cursor(ctx, nb);
-  DevBuf<uint32_t> bsums(ctx, nblk + 1);
-  DevBuf<uint32_t> entries(ctx, (size_t)n * tab.nwin);
-
-  KB_CUDA(cudaMemsetAsync(counts, 0, nb * sizeof(uint32_t), ctx->stream));
-  KB_LAUNCH(ctx, msm_count_kernel, cdiv(n, 256), 256, 0, d_scalars, n, c, tab.nwin, counts);
-  KB_LAUNCH(ctx, scan_local_kernel, nblk, 256, 0, counts, offsets, bsums, nb);
-  KB_LAUNCH(ctx, scan_sums_kernel, 1, 32, 0, bsums, nblk);
-  KB_LAUNCH(ctx, scan_add_kernel, cdiv(nb + 1, 256), 256, 0, offsets, bsums, cursor, nb, nblk);
-  KB_LAUNCH(ctx, msm_scatter_kernel, cdiv(n, 256), 256, 0, d_scalars, n, c, tab.nwin, cursor, entries);
-  DevBuf<uint32_t> size_bins(ctx, MSM_SIZE_BINS);
-  DevBuf<uint32_t> perm(ctx, nb);
-  KB_CUDA(cudaMemsetAsync(size_bins, 0, MSM_SIZE_BINS * sizeof(uint32_t), ctx->stream));
-  KB_LAUNCH(ctx, msm_size_hist_kernel, cdiv(nb, 256), 256, 0, offsets, nb, size_bins);
-  KB_LAUNCH(ctx, msm_size_scan_kernel, 1, MSM_SIZE_BINS, 0, size_bins);
-  KB_LAUNCH(ctx, msm_size_scatter_kernel, cdiv(nb, 256), 256, 0, offsets, nb, size_bins, perm);
-  timer_start(ctx, KB_T_MSM_ACC);
-  launch_msm_accumulate(ctx, tab.d, tab.n, first, offsets, entries, perm, nb, buckets, into);
-  timer_stop(ctx, KB_T_MSM_ACC);
+  const uint64_t n = w.n;
+  KB_CUDA(cudaMemsetAsync(w.counts, 0, nb * sizeof(uint32_t), st));
+  KB_LAUNCH_ON(ctx, st, msm_count_kernel, cdiv(n, 256), 256, 0, d_scalars, n, c, tab.nwin, w.counts);
+  KB_LAUNCH_ON(ctx, st, scan_local_kernel, nblk, 256, 0, w.counts, w.offsets, w.bsums, nb);
+  KB_LAUNCH_ON(ctx, st, scan_sums_kernel, 1, 32, 0, w.bsums, nblk);
+  KB_LAUNCH_ON(ctx, st, scan_add_kernel, cdiv(nb + 1, 256), 256, 0, w.offsets, w.bsums, w.cursor, nb, nblk);
+  KB_LAUNCH_ON(ctx, st, msm_scatter_kernel, cdiv(n, 256), 256, 0, d_scalars, n, c, tab.nwin, w.cursor, w.entries);
+  KB_CUDA(cudaMemsetAsync(w.size_bins, 0, MSM_SIZE_BINS * sizeof(uint32_t), st));
+  KB_LAUNCH_ON(ctx, st, msm_size_hist_kernel, cdiv(nb, 256), 256, 0, w.offsets, nb, w.size_bins);
+  KB_LAUNCH_ON(ctx, st, msm_size_scan_kernel, 1, MSM_SIZE_BINS, 0, w.size_bins);
+  KB_LAUNCH_ON(ctx, st, msm_size_scatter_kernel, cdiv(nb, 256), 256, 0, w.offsets, nb, w.size_bins, w.perm);
 }
 
 static void msm_empty(kb_ctx* ctx, uint32_t* d_out_xy, uint8_t* d_out_inf) {
@@ -237,50 +238,68 @@ static void msm_empty(kb_ctx* ctx, uint32_t* d_out_xy, uint8_t* d_out_inf) {
   if (d_out_inf) KB_CUDA(cudaMemsetAsync(d_out_inf, 1, 1, ctx->stream));
 }
 
-void msm_g1(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t first, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
+// Scalars at `scalars`: device memory, or host memory when `from_host` (the reference-facing call: `commit` hands over
+// a Vec<Fr>).  Large host inputs run as TWO passes over one bucket set (all windows of a point share it, so any split of
+// the point range is valid): the first quarter of the points is copied, sorted and accumulated while the side stream
+// copies and sorts the rest; the second accumulation adds onto the same buckets; one bucket reduction at the end.
+// (Measured: for resident inputs the split does not pay - the second sort only partly hides under the first
+// accumulation and two accumulations over half-filled buckets cost what it saves - so they take one pass.)
+static void msm_run(kb_ctx* ctx, const uint32_t* scalars, bool from_host, uint64_t first, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
   if (n == 0) return msm_empty(ctx, d_out_xy, d_out_inf);
   if (n > (1ull << 26)) throw ApiError(KB_ERR_ARG, "kb_msm_g1: more than 2^26 points in one call");
   const int c = msm_choose_c(first + n);
   const MsmTable& tab = msm_get_table(ctx, c);
   const uint32_t nb = 1u << (c - 1);
+  DevBuf<uint32_t> staged(ctx, from_host ? (size_t)n * 8 : 0);
+  const uint32_t* d_sc = from_host ? staged.p : scalars;
   DevBuf<uint32_t> buckets(ctx, 32 * (size_t)nb);
-  msm_pass(ctx, tab, c, d_scalars, first, n, buckets, false);
-  launch_msm_reduce(ctx, buckets, nb, d_out_xy, d_out_inf);
-}
-
-// Scalars in HOST memory (the reference-facing call: `commit` hands over a Vec<Fr>): the host-to-device copy of the
-// scalars is pipelined with the computation.  The first quarter of the points is copied, then sorted and accumulated
-// while the copy engine brings the rest; the second pass adds onto the same buckets (all windows of a point share the
-// one bucket set, so any split of the point range is valid); one bucket reduction at the end.
-void msm_g1_host(kb_ctx* ctx, const uint32_t* h_scalars, uint64_t first, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
-  if (n == 0) return msm_empty(ctx, d_out_xy, d_out_inf);
-  if (n > (1ull << 26)) throw ApiError(KB_ERR_ARG, "kb_msm_g1: more than 2^26 points in one call");
-  DevBuf<uint32_t> sc(ctx, (size_t)n * 8);
-  if (n < (1ull << 18)) {   // small inputs: one copy, one pass
-    KB_CUDA(cudaMemcpyAsync(sc, h_scalars, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    return msm_g1(ctx, sc, first, n, d_out_xy, d_out_inf);
+  if (!from_host || n < (1ull << 18)) {   // resident or small inputs: (one copy,) one pass
+    if (from_host) KB_CUDA(cudaMemcpyAsync(staged, scalars, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    MsmSort w(ctx, nb, n, tab.nwin);
+    msm_sort(ctx, ctx->stream, w, tab, c, d_sc);
+    timer_start(ctx, KB_T_MSM_ACC);
+    launch_msm_accumulate(ctx, tab.d, tab.n, first, w.offsets, w.entries, w.perm, nb, buckets, false);
+    timer_stop(ctx, KB_T_MSM_ACC);
+    launch_msm_reduce(ctx, buckets, nb, d_out_xy, d_out_inf);
+    return;
   }
-  const int c = msm_choose_c(first + n);
-  const MsmTable& tab = msm_get_table(ctx, c);
-  const uint32_t nb = 1u << (c - 1);
-  const uint64_t na = n / 4;
-  KB_CUDA(cudaEventRecord(ctx->ev_copy[0], ctx->stream));                     // the scratch allocation is ordered on the main stream
-  KB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[0], 0));
-  KB_CUDA(cudaMemcpyAsync(sc, h_scalars, (size_t)na * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-  KB_CUDA(cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
-  KB_CUDA(cudaMemcpyAsync(sc.p + 8 * na, h_scalars + 8 * na, (size_t)(n - na) * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-  KB_CUDA(cudaEventRecord(ctx->ev_copy[2], ctx->copy_stream));
+  const uint64_t na = n / 4, nbp = n - na;
+  MsmSort wa(ctx, nb, na, tab.nwin), wb(ctx, nb, nbp, tab.nwin);
+  cudaStream_t side = ctx->copy_stream;
   try {
-    DevBuf<uint32_t> buckets(ctx, 32 * (size_t)nb);
-    KB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));
-    msm_pass(ctx, tab, c, sc, first, na, buckets, false);
+    KB_CUDA(cudaEventRecord(ctx->ev_copy[0], ctx->stream));      // scratch allocations and the table are ordered on the main stream
+    KB_CUDA(cudaStreamWaitEvent(side, ctx->ev_copy[0], 0));
+    if (from_host) {
+      KB_CUDA(cudaMemcpyAsync(staged, scalars, (size_t)na * 32, cudaMemcpyHostToDevice, side));
+      KB_CUDA(cudaEventRecord(ctx->ev_copy[1], side));
+      KB_CUDA(cudaMemcpyAsync(staged.p + 8 * na, scalars + 8 * na, (size_t)nbp * 32, cudaMemcpyHostToDevice, side));
+      KB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));
+    }
+    msm_sort(ctx, ctx->stream, wa, tab, c, d_sc);                 // main stream: sort of the first pass
+    // the second sort is L2-bound like the first (they would only share the L2 if run together) but overlaps well with
+    // the multiplier-bound accumulation: gate it behind the first sort; the side stream has the higher priority, so its
+    // blocks are dispatched as accumulation blocks retire
+    KB_CUDA(cudaEventRecord(ctx->ev_copy[3], ctx->stream));
+    KB_CUDA(cudaStreamWaitEvent(side, ctx->ev_copy[3], 0));
+    msm_sort(ctx, side, wb, tab, c, d_sc + 8 * na);
+    KB_CUDA(cudaEventRecord(ctx->ev_copy[2], side));
+    timer_start(ctx, KB_T_MSM_ACC);
+    launch_msm_accumulate(ctx, tab.d, tab.n, first, wa.offsets, wa.entries, wa.perm, nb, buckets, false);
     KB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[2], 0));
-    msm_pass(ctx, tab, c, sc.p + 8 * na, first + na, n - na, buckets, true);
+    launch_msm_accumulate(ctx, tab.d, tab.n, first + na, wb.offsets, wb.entries, wb.perm, nb, buckets, true);
+    timer_stop(ctx, KB_T_MSM_ACC);
     launch_msm_reduce(ctx, buckets, nb, d_out_xy, d_out_inf);
   } catch (...) {
-    cudaStreamSynchronize(ctx->copy_stream);   // the scratch buffer must outlive the copies in flight
+    cudaStreamSynchronize(side);   // the scratch buffers must outlive the work in flight on the side stream
     throw;
   }
+}
+
+void msm_g1(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t first, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
+  msm_run(ctx, d_scalars, false, first, n, d_out_xy, d_out_inf);
+}
+void msm_g1_host(kb_ctx* ctx, const uint32_t* h_scalars, uint64_t first, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf) {
+  msm_run(ctx, h_scalars, true, first, n, d_out_xy, d_out_inf);
 }
 
 // ------------------------------------------------------------------------------------------
