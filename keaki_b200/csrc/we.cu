@@ -273,39 +273,66 @@ void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const
 }
 
 // ------------------------------------------------------------------------------------------
-// verify: e(C - v G1, G2) * e(-pi, tau_2 - a G2) == 1   (src/kzg.rs:127-151)
+// verify (src/kzg.rs:127-151): e(C - v G1, G2) == e(pi, tau_2 - a G2), as the reference computes it - two pairings per
+// item and a comparison.  The operands are prepared per item (generic G1 multiplication of the generator, fixed-base G2
+// multiplication from the 16-bit-window table), the 2n pairings run on the pairing VM, the GT images are compared.
+// A pair with a point at infinity gives GT = 1 exactly as in arkworks (the VM kernel's `trivial` path).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) verify_kernel(const uint32_t* __restrict__ com, const uint8_t* __restrict__ com_inf,
-                                                     const uint32_t* __restrict__ points, const uint32_t* __restrict__ values,
-                                                     const uint32_t* __restrict__ proofs, const uint8_t* __restrict__ pinf,
-                                                     const uint32_t* __restrict__ tau2_xy, const uint32_t* __restrict__ g2_gen,
-                                                     const uint32_t* __restrict__ g1_gen, uint64_t n, uint8_t* __restrict__ ok) {
+__global__ void __launch_bounds__(128) verify_prep_kernel(const uint32_t* __restrict__ com, const uint8_t* __restrict__ com_inf,
+                                                          const uint32_t* __restrict__ points, const uint32_t* __restrict__ values,
+                                                          const uint32_t* __restrict__ proofs, const uint8_t* __restrict__ pinf,
+                                                          const uint32_t* __restrict__ tau2_xy, const uint32_t* __restrict__ g2_tab16,
+                                                          const uint32_t* __restrict__ g2_gen, const uint32_t* __restrict__ g1_gen, uint64_t n,
+                                                          uint32_t* __restrict__ g1 /* 2n */, uint8_t* __restrict__ g1_inf,
+                                                          uint32_t* __restrict__ g2 /* 2n */, uint8_t* __restrict__ g2_inf) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fr kv = fp_from_mont<FrParams>(fp_load<FrParams>(values + 8 * i));
   Fr ka = fp_from_mont<FrParams>(fp_load<FrParams>(points + 8 * i));
-  G1Affine c = load_g1_flag(com, com_inf, i);
-  G1Affine pi = load_g1_flag(proofs, pinf, i);
-  G2Affine g2 = ld_g2(g2_gen);
+  // commitment - [value]_1
   G1 vg = ec_mul(to_xyzz(ld_g1(g1_gen)), kv.v);
-  G1Affine lhs = to_affine(ec_add(to_xyzz(c), neg(vg)));
-  G2 ag = ec_mul(to_xyzz(g2), ka.v);
-  G2Affine rhs = to_affine(ec_add(to_xyzz(ld_g2(tau2_xy)), neg(ag)));
-  pi.y = -pi.y;
-  Fq12 f = miller_loop(lhs, g2, c_pc) * miller_loop(pi, rhs, c_pc);
-  Fq12 e = final_exponentiation(f, c_pc);
-  ok[i] = (e == Fq12::one()) ? 1 : 0;
+  G1 lhs = ec_add(to_xyzz(load_g1_flag(com, com_inf, i)), neg(vg));
+  st_g1(g1 + 16 * i, to_affine(lhs));
+  g1_inf[i] = lhs.is_inf() ? 1 : 0;
+  st_g2(g2 + 32 * i, ld_g2(g2_gen));
+  g2_inf[i] = 0;
+  // proof, [tau]_2 - [point]_2
+  G1Affine pi = load_g1_flag(proofs, pinf, i);
+  st_g1(g1 + 16 * (n + i), pi);
+  g1_inf[n + i] = pi.is_inf() ? 1 : 0;
+  G2 acc = to_xyzz(ld_g2(tau2_xy));
+  for (int w = 0; w < WE_WIN16; w++) {
+    uint32_t d = half_of(ka.v, w);
+    if (d) { G2Affine t = ld_g2(g2_tab16 + 32 * ((size_t)w * WE_ENT16 + d - 1)); t.y = -t.y; acc = ec_add_mixed(acc, t); }
+  }
+  st_g2(g2 + 32 * (n + i), to_affine(acc));
+  g2_inf[n + i] = acc.is_inf() ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) gt_pairs_equal_kernel(const uint32_t* __restrict__ gt /* 2n x 96 words */, uint64_t n, uint8_t* __restrict__ ok) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4* a = reinterpret_cast<const uint4*>(gt + 96 * i);
+  const uint4* b = reinterpret_cast<const uint4*>(gt + 96 * (n + i));
+  uint32_t diff = 0;
+#pragma unroll 4
+  for (int k = 0; k < 24; k++) { uint4 x = a[k], y = b[k]; diff |= (x.x ^ y.x) | (x.y ^ y.y) | (x.z ^ y.z) | (x.w ^ y.w); }
+  ok[i] = diff == 0 ? 1 : 0;
 }
 
 void verify_batch(kb_ctx* ctx, const uint32_t* d_com, const uint8_t* d_com_inf, const uint32_t* d_points, const uint32_t* d_values,
                   const uint32_t* d_proofs, const uint8_t* d_pinf, uint64_t n, uint8_t* d_ok) {
   if (!n) return;
-  DevBuf<uint32_t> g2(ctx, 32), g1(ctx, 16);
-  KB_CUDA(cudaMemcpyAsync(g2, consts::G2_GEN, 128, cudaMemcpyHostToDevice, ctx->stream));
-  KB_CUDA(cudaMemcpyAsync(g1, consts::G1_GEN, 64, cudaMemcpyHostToDevice, ctx->stream));
+  DevBuf<uint32_t> g2gen(ctx, 32), g1gen(ctx, 16);
+  KB_CUDA(cudaMemcpyAsync(g2gen, consts::G2_GEN, 128, cudaMemcpyHostToDevice, ctx->stream));
+  KB_CUDA(cudaMemcpyAsync(g1gen, consts::G1_GEN, 64, cudaMemcpyHostToDevice, ctx->stream));
+  DevBuf<uint32_t> g1(ctx, 16 * 2 * n), g2(ctx, 32 * 2 * n), gt(ctx, 96 * 2 * n);
+  DevBuf<uint8_t> g1i(ctx, 2 * n), g2i(ctx, 2 * n);
   // tau_2 itself is entry (w = 0, d = 1) of its fixed-base table
-  KB_LAUNCH(ctx, verify_kernel, cdiv(n, 128), 128, 0, d_com, d_com_inf, d_points, d_values, d_proofs, d_pinf,
-            ctx->d_tau2_tab, g2, g1, n, d_ok);
+  KB_LAUNCH(ctx, verify_prep_kernel, cdiv(n, 128), 128, 0, d_com, d_com_inf, d_points, d_values, d_proofs, d_pinf,
+            ctx->d_tau2_tab, ctx->d_g2_tab16, g2gen.p, g1gen.p, n, g1.p, g1i.p, g2.p, g2i.p);
+  pairing_batch(ctx, g1, g1i, g2, g2i, 2 * n, reinterpret_cast<uint8_t*>(gt.p));
+  KB_LAUNCH(ctx, gt_pairs_equal_kernel, cdiv(n, 256), 256, 0, gt.p, n, d_ok);
 }
 
 }  // namespace kb
