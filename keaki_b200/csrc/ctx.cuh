@@ -7,6 +7,7 @@
 #include <stdexcept>
 #include "../../include/keaki_b200.h"
 #include "pairing.cuh"
+#include "glv.cuh"
 
 namespace kb {
 

@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(128) srs_generate_kernel(const uint32_t* __res
   G1Affine g;
   g.x = Fq::one();
   g.y = Fq::one() + Fq::one();
-  st_g1(out + 16 * i, to_affine(ec_mul(to_xyzz(g), k.v)));
+  st_g1(out + 16 * i, to_affine(g1_mul_glv(to_xyzz(g), k.v)));
 }
 
 __global__ void srs_tau_g2_kernel(const uint32_t* __restrict__ tau_m, const uint32_t* __restrict__ g2_gen, uint32_t* __restrict__ out) {
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(128) g1_mul_gen_kernel(const uint32_t* __restr
   G1Affine g;
   g.x = Fq::one();
   g.y = Fq::one() + Fq::one();
-  G1 r = ec_mul(to_xyzz(g), k.v);
+  G1 r = g1_mul_glv(to_xyzz(g), k.v);
   st_g1(out_xy + 16 * i, to_affine(r));
   out_inf[i] = r.is_inf() ? 1 : 0;
 }

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(128) g1_butterfly_kernel(uint32_t* __restrict_
     uint32_t kk[8];
     const uint32_t* src = tw_canon + 8 * (size_t)(k << (logn - 1 - s));
     for (int q = 0; q < 8; q++) kk[q] = src[q];
-    v = ec_mul(v, kk);
+    v = g1_mul_glv(v, kk);
   }
   st_g1x(a + 32 * (size_t)i, ec_add(u, v));
   st_g1x(a + 32 * (size_t)j, ec_add(u, neg(v)));
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128) fk_pointwise_kernel(const uint32_t* __res
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n2) return;
   Fr k = fp_from_mont<FrParams>(fp_load<FrParams>(hat_a + 8 * (size_t)i) * fp_load<FrParams>(inv2d));
-  st_g1x(out + 32 * (size_t)i, ec_mul(ld_g1x(hat_s + 32 * (size_t)i), k.v));
+  st_g1x(out + 32 * (size_t)i, g1_mul_glv(ld_g1x(hat_s + 32 * (size_t)i), k.v));
 }
 __global__ void __launch_bounds__(128) g1_xyzz_to_affine_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out_xy,
                                                                 uint8_t* __restrict__ out_inf) {

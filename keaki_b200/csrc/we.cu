@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(128) verify_prep_kernel(const uint32_t* __rest
   Fr kv = fp_from_mont<FrParams>(fp_load<FrParams>(values + 8 * i));
   Fr ka = fp_from_mont<FrParams>(fp_load<FrParams>(points + 8 * i));
   // commitment - [value]_1
-  G1 vg = ec_mul(to_xyzz(ld_g1(g1_gen)), kv.v);
+  G1 vg = g1_mul_glv(to_xyzz(ld_g1(g1_gen)), kv.v);
   G1 lhs = ec_add(to_xyzz(load_g1_flag(com, com_inf, i)), neg(vg));
   st_g1(g1 + 16 * i, to_affine(lhs));
   g1_inf[i] = lhs.is_inf() ? 1 : 0;

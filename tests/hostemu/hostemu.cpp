@@ -10,6 +10,7 @@
 #include <thread>
 #include <vector>
 #include "../../keaki_b200/csrc/pairing.cuh"
+#include "../../keaki_b200/csrc/glv.cuh"
 #include "../../keaki_b200/csrc/blake3.cuh"
 #include "../../keaki_b200/csrc/consts_gen.cuh"
 #include "../../keaki_b200/csrc/msm_digits.cuh"
@@ -104,6 +105,17 @@ void he_g1_lincomb(const uint32_t* p_xy, const uint32_t* k1, const uint32_t* q_x
   G1Affine p, q; p.x = ldq(p_xy); p.y = ldq(p_xy + 8); q.x = ldq(q_xy); q.y = ldq(q_xy + 8);
   G1Affine a = to_affine(ec_add(ec_mul(to_xyzz(p), k1), ec_mul(to_xyzz(q), k2)));
   stq(out_xy, a.x); stq(out_xy + 8, a.y);
+}
+// GLV path: out_xy = k * P by g1_mul_glv; split (optional, 12 words) = m1[5], m2[5], neg1, neg2 of glv_decompose(k)
+void he_g1_mul_glv(const uint32_t* p_xy, const uint32_t* k, uint32_t* out_xy, uint32_t* split) {
+  G1Affine p; p.x = ldq(p_xy); p.y = ldq(p_xy + 8);
+  G1Affine a = to_affine(g1_mul_glv(to_xyzz(p), k));
+  stq(out_xy, a.x); stq(out_xy + 8, a.y);
+  if (split) {
+    GlvSplit s = glv_decompose(k);
+    for (int i = 0; i < 5; i++) { split[i] = s.m1[i]; split[5 + i] = s.m2[i]; }
+    split[10] = s.neg1; split[11] = s.neg2;
+  }
 }
 void he_g2_mul_add(const uint32_t* p_xy, const uint32_t* k, const uint32_t* q_xy, uint32_t* out_xy) {
   G2Affine p; p.x = ldq2(p_xy); p.y = ldq2(p_xy + 16);

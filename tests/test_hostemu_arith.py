@@ -183,3 +183,32 @@ def test_binary_inversion_edge_representations():
             out = np.zeros(8, np.uint32)
             he.he_fp_op(field, 4, P(A), P(A), P(out), 1)
             assert bn.from_mont(L.limbs_to_int(out), mod) == pow(a, -1, mod), (field, am)
+
+
+def test_glv_scalar_multiplication_on_g1():
+    """glv.cuh: the division-free decomposition k = k1 + k2 lambda (|k1|, |k2| < 2^128, congruence mod r) and
+    k * P by the shared-table double scalar multiplication, against the oracle's plain double-and-add."""
+    import os
+    import re
+    txt = open(os.path.join(os.path.dirname(__file__), "..", "keaki_b200", "csrc", "glv_gen.cuh")).read()
+
+    def table(name):
+        body = re.search(r"KB_LIMB_TABLE\(%s, ([^)]*)\)" % name, txt).group(1)
+        return sum(int(x.strip().rstrip("u"), 16) << (32 * i) for i, x in enumerate(body.split(",")))
+    lam, beta = table("lambda"), bn.from_mont(table("beta"), bn.Q)
+    assert pow(lam, 3, bn.R) == 1 and lam != 1 and pow(beta, 3, bn.Q) == 1 and beta != 1
+    a1, a2, b1, b2 = table("a1"), table("a2"), table("b1abs"), table("b2")
+    assert (a1 - b1 * lam) % bn.R == 0 and (a2 + b2 * lam) % bn.R == 0 and a1 * b2 + a2 * b1 == bn.R
+    assert table("g1c") == (b2 << 256) // bn.R and table("g2c") == (b1 << 256) // bn.R
+    P0 = bn.g1_mul(bn.G1_GEN, 0xDEADBEEFCAFE)
+    assert ((beta * P0[0]) % bn.Q, P0[1]) == bn.g1_mul(P0, lam)             # phi(P) = lambda P
+    ks = [0, 1, 2, 3, bn.R - 1, bn.R - 2, lam, lam - 1, lam + 1, bn.R // 2, 1 << 253, 1 << 128, (1 << 128) - 1, 1 << 127] + [rng.randrange(bn.R) for _ in range(40)]
+    A = L.g1_m(P0)
+    for k in ks:
+        out = np.zeros(16, np.uint32); split = np.zeros(12, np.uint32)
+        he.he_g1_mul_glv(P(A), P(L.int_to_limbs(k)), P(out), P(split))
+        m1, m2 = L.limbs_to_int(split[:5]), L.limbs_to_int(split[5:10])
+        s1 = -m1 if split[10] else m1
+        s2 = -m2 if split[11] else m2
+        assert m1 < (1 << 128) and m2 < (1 << 128) and (s1 + s2 * lam - k) % bn.R == 0, k
+        assert L.g1_from(out) == bn.g1_mul(P0, k), k
