@@ -53,6 +53,8 @@ struct kb_ctx {
   bool com_tab_valid = false;
   uint32_t* d_com_tab16 = nullptr;   // 16-bit-window table of the cached commitment, built once it has served 2^15 messages
   bool com_tab16_valid = false;
+  uint32_t* d_com1_tab = nullptr;    // the same two tables for A' = e(com - G1, G2) = A / gT: messages with value = 1
+  uint32_t* d_com1_tab16 = nullptr;  //   (laconic OT: every value is a bit) need A'^r only
   uint64_t com_msgs = 0;             // messages encrypted under the cached commitment so far
 
   // pairing VM (pairing_vm.cu): program + constants resident on the device

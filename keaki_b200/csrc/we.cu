@@ -155,6 +155,7 @@ void we_init_tables(kb_ctx* ctx) {
   KB_CUDA(cudaMalloc((void**)&ctx->d_tau2_tab, G2_TAB_LIMBS * 4));
   KB_CUDA(cudaMalloc((void**)&ctx->d_gt_tab, GT_TAB_LIMBS * 4));
   KB_CUDA(cudaMalloc((void**)&ctx->d_com_tab, GT_TAB_LIMBS * 4));
+  KB_CUDA(cudaMalloc((void**)&ctx->d_com1_tab, GT_TAB_LIMBS * 4));
   DevBuf<uint32_t> g2(ctx, 32), g1(ctx, 16), gt(ctx, 96);
   KB_CUDA(cudaMemcpyAsync(g2, consts::G2_GEN, 128, cudaMemcpyHostToDevice, ctx->stream));
   KB_CUDA(cudaMemcpyAsync(g1, consts::G1_GEN, 64, cudaMemcpyHostToDevice, ctx->stream));
@@ -178,6 +179,9 @@ void we_free(kb_ctx* ctx) {
   cudaFree(ctx->d_g2_tab); cudaFree(ctx->d_tau2_tab); cudaFree(ctx->d_gt_tab); cudaFree(ctx->d_com_tab);
   cudaFree(ctx->d_g2_tab16); cudaFree(ctx->d_tau2_tab16); cudaFree(ctx->d_gt_tab16);
   if (ctx->d_com_tab16) cudaFree(ctx->d_com_tab16);
+  if (ctx->d_com1_tab16) cudaFree(ctx->d_com1_tab16);
+  cudaFree(ctx->d_com1_tab);
+  ctx->d_com1_tab = ctx->d_com1_tab16 = nullptr;
   ctx->d_com_tab16 = nullptr; ctx->com_tab16_valid = false;
   ctx->d_g2_tab = ctx->d_tau2_tab = ctx->d_gt_tab = ctx->d_com_tab = nullptr;
   ctx->d_g2_tab16 = ctx->d_tau2_tab16 = ctx->d_gt_tab16 = nullptr;
@@ -192,8 +196,8 @@ __device__ __forceinline__ uint32_t half_of(const uint32_t* k, int w) { return (
 // Two kernels per batch: the GT side (two fixed-base exponentiations, hash, XOR) keeps an Fq12 accumulator and a table
 // entry live (255 registers); the G2 side (two fixed-base multiplications, one affine normalisation) needs a third of
 // that, so it runs at three times the occupancy in a kernel of its own.
-__global__ void __launch_bounds__(128) encrypt_kernel(const uint32_t* __restrict__ com_tab, const uint32_t* __restrict__ gt_tab,
-                                                      const uint32_t* __restrict__ values, const uint32_t* __restrict__ rs,
+__global__ void __launch_bounds__(128) encrypt_kernel(const uint32_t* __restrict__ com_tab_a, const uint32_t* __restrict__ com_tab_a1,
+                                                      const uint32_t* __restrict__ gt_tab, const uint32_t* __restrict__ values, const uint32_t* __restrict__ rs,
                                                       const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off, uint64_t n, int com_wide,
                                                       uint8_t* __restrict__ msg_ct) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -201,7 +205,11 @@ __global__ void __launch_bounds__(128) encrypt_kernel(const uint32_t* __restrict
   Fr r = fp_load<FrParams>(rs + 8 * i);
   Fr v = fp_load<FrParams>(values + 8 * i);
   Fr kr = fp_from_mont<FrParams>(r);             // r
-  Fr ks = fp_from_mont<FrParams>(-(v * r));      // -v r
+  // value = 0: secret = A^r; value = 1: secret = (A / gT)^r from the second per-commitment table (the values of a
+  // laconic-OT sender are bits, tests/laconic_ot.rs:89-109); any other value takes the general form below
+  const bool v_one = v == Fr::one(), v_bit = v_one || v.is_zero();
+  const uint32_t* com_tab = v_one ? com_tab_a1 : com_tab_a;
+  Fr ks = v_bit ? Fr::zero() : fp_from_mont<FrParams>(-(v * r));      // -v r
 
   // secret = A^r * gT^(-v r): 8- or 16-bit windows for A (per-commitment table), 16-bit windows for gT
   Fq12 s = Fq12::one();
@@ -248,6 +256,12 @@ __global__ void __launch_bounds__(128, 3) encrypt_ct_kernel(const uint32_t* __re
   ct_inf[i] = acc.is_inf() ? 1 : 0;
 }
 
+// a1 = a * conj(gT)  (gT is unitary: the conjugate is the inverse), gT = entry (window 0, digit 1) of its table
+__global__ void gt_div_gen_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ gt_tab, uint32_t* __restrict__ a1) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st_fq12(a1, ld_fq12(a) * conj(ld_fq12(gt_tab)));
+}
+
 void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const uint32_t* d_points, const uint32_t* d_values,
                    const uint32_t* d_r, const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n,
                    uint32_t* d_ct, uint8_t* d_ct_inf, uint8_t* d_msg_ct) {
@@ -262,6 +276,9 @@ void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const
     KB_CUDA(cudaMemcpyAsync(g2, consts::G2_GEN, 128, cudaMemcpyHostToDevice, ctx->stream));
     KB_LAUNCH(ctx, pairing_with_g2gen_kernel, 1, 32, 0, com, key[16], g2, a);
     build_gt_table(ctx, a, ctx->d_com_tab);
+    DevBuf<uint32_t> a1(ctx, 96);
+    KB_LAUNCH(ctx, gt_div_gen_kernel, 1, 32, 0, a.p, ctx->d_gt_tab, a1.p);
+    build_gt_table(ctx, a1, ctx->d_com1_tab);
     memcpy(ctx->com_cached, key, sizeof(key));
     ctx->com_tab_valid = true;
     ctx->com_tab16_valid = false;
@@ -271,13 +288,15 @@ void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const
   if (!ctx->com_tab16_valid && ctx->com_msgs >= (1ull << 15)) {
     if (!ctx->d_com_tab16) KB_CUDA(cudaMalloc((void**)&ctx->d_com_tab16, GT_TAB16_LIMBS * 4));
     KB_LAUNCH(ctx, gt_table16_kernel, cdiv((uint64_t)WE_WIN16 * WE_ENT16, 128), 128, 0, ctx->d_com_tab, ctx->d_com_tab16);
+    if (!ctx->d_com1_tab16) KB_CUDA(cudaMalloc((void**)&ctx->d_com1_tab16, GT_TAB16_LIMBS * 4));
+    KB_LAUNCH(ctx, gt_table16_kernel, cdiv((uint64_t)WE_WIN16 * WE_ENT16, 128), 128, 0, ctx->d_com1_tab, ctx->d_com1_tab16);
     ctx->com_tab16_valid = true;
   }
   ctx->com_msgs += n;
   const bool wide = ctx->com_tab16_valid;
   timer_start(ctx, KB_T_ENCRYPT);
-  KB_LAUNCH(ctx, encrypt_kernel, cdiv(n, 128), 128, 0, wide ? ctx->d_com_tab16 : ctx->d_com_tab, ctx->d_gt_tab16,
-            d_values, d_r, d_msgs, d_off, n, wide ? 1 : 0, d_msg_ct);
+  KB_LAUNCH(ctx, encrypt_kernel, cdiv(n, 128), 128, 0, wide ? ctx->d_com_tab16 : ctx->d_com_tab, wide ? ctx->d_com1_tab16 : ctx->d_com1_tab,
+            ctx->d_gt_tab16, d_values, d_r, d_msgs, d_off, n, wide ? 1 : 0, d_msg_ct);
   KB_LAUNCH(ctx, encrypt_ct_kernel, cdiv(n, 128), 128, 0, ctx->d_tau2_tab16, ctx->d_g2_tab16, d_points, d_r, n, d_ct, d_ct_inf);
   timer_stop(ctx, KB_T_ENCRYPT);
 }

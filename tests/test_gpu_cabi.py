@@ -220,6 +220,8 @@ def test_encrypt_decrypt_bit_exact(ctx, srs):
     points[0] = 0
     values = [kr.poly_eval(p, z) for z in points]
     values[1] = 0                       # wrong value (and the value = 0 edge: beta*G1 = identity)
+    values[9] = 1                       # value = 1 takes the second per-commitment table (A / gT)^r, value = 2 the general form
+    values[10] = 2
     rs = [rng.randrange(bn.R) for _ in range(n)]
     rs[2] = 0                           # r = 0: ciphertext is the identity, key = H(1)
     rs[3] = 1
@@ -245,7 +247,7 @@ def test_encrypt_decrypt_bit_exact(ctx, srs):
     for i in range(n):
         got = bytes(out[int(off[i]): int(off[i + 1])])
         assert got == ref[i], f"dec {i}"
-        if i != 1:
+        if i not in (1, 9, 10):
             assert got == msgs[i]
     assert bytes(out[int(off[1]): int(off[2])]) != msgs[1]   # wrong value -> garbage (src/enc.rs:99-125)
     # commitment at infinity and commitment == value*G1 (com_beta = identity): key = H(1)
