@@ -2,10 +2,13 @@
 // tests/laconic_ot.rs:114-200) re-instantiated on BN254 against the C++ host layer (include/keaki_b200.hpp) —
 // every group, pairing and transform operation below runs in libkeaki_b200.so on the GPU.
 //
-//   test_keaki_host [path/to/ppot_0080_01_mini.ptau]
+//   test_keaki_host [path/to/ppot_0080_01_mini.ptau [path/to/oracle_vectors.txt]]
 // exit codes: 0 all passed, 1 a check failed, 3 no usable GPU (the product path has no CPU fallback).
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <map>
+#include <sstream>
 #include <string>
 #include "../../include/keaki_b200.hpp"
 
@@ -196,8 +199,65 @@ static void test_new_from_file_and_config1() {
   CHECK(threw);
 }
 
+// ---------------------------------------------------------------------------------------------- committed golden bytes
+// tests/golden/oracle_vectors.txt (written by tests/golden/make_golden.py from the oracle): the C++ layer must
+// reproduce the oracle's commitment, FK proofs, ciphertext points and masked messages byte for byte.
+static std::string g_golden;
+static Bytes unhex(const std::string& h) {
+  Bytes b;
+  if (h == "-") return b;
+  for (size_t i = 0; i + 1 < h.size(); i += 2) b.push_back((uint8_t)std::stoul(h.substr(i, 2), nullptr, 16));
+  return b;
+}
+static Fr fr_from_le(const Bytes& b) { uint64_t c[4]; std::memcpy(c, b.data(), 32); return Fr::from_canonical(c); }
+struct FixedRng {   // hands out prepared field elements through the `Fr::rand` protocol (four limbs of the Montgomery form)
+  std::vector<Fr> xs; size_t i = 0, k = 0;
+  uint64_t next_u64() { uint64_t v = xs.at(i).l[k]; if (++k == 4) { k = 0; i++; } return v; }
+};
+static Bytes g1_bytes(const KZGSetup& s, const G1& p) {
+  Bytes out(64); uint8_t inf = p.inf;
+  detail::check(s.ctx(), kb_g1_serialize(s.ctx(), p.xy, &inf, 1, 0, out.data()), "kb_g1_serialize");
+  return out;
+}
+static Bytes g2_bytes(const KZGSetup& s, const G2& p) {
+  Bytes out(128); uint8_t inf = p.inf;
+  detail::check(s.ctx(), kb_g2_serialize(s.ctx(), p.xy, &inf, 1, 0, out.data()), "kb_g2_serialize");
+  return out;
+}
+static void test_golden_vectors() {
+  std::ifstream f(g_golden);
+  CHECK(f.good());
+  std::map<std::string, std::vector<Bytes>> v;
+  for (std::string line; std::getline(f, line);) {
+    std::istringstream ss(line);
+    std::string key, tok;
+    ss >> key;
+    while (ss >> tok) v[key].push_back(unhex(tok));
+  }
+  Fr tau = fr_from_le(v["tau"].at(0));
+  std::vector<Fr> p, points, values;
+  for (auto& b : v["coeffs"]) p.push_back(fr_from_le(b));
+  for (auto& b : v["points"]) points.push_back(fr_from_le(b));
+  for (auto& b : v["values"]) values.push_back(fr_from_le(b));
+  KZGSetup s = KZGSetup::setup(tau, p.size());
+  G1 com = commit(s, p);
+  CHECK(g1_bytes(s, com) == v["commitment"].at(0));
+  std::vector<G1> proofs = open_fk(s, p, Radix2EvaluationDomain(p.size()));
+  CHECK(proofs.size() == v["proofs"].size());
+  for (size_t i = 0; i < proofs.size(); i++) CHECK(g1_bytes(s, proofs[i]) == v["proofs"][i]);
+  FixedRng rng;
+  for (auto& b : v["r"]) rng.xs.push_back(fr_from_le(b));
+  std::vector<Ciphertext> cts = vec_encrypt(rng, s, com, points, values, v["messages"]);
+  CHECK(cts.size() == v["ct"].size());
+  for (size_t i = 0; i < cts.size(); i++) { CHECK(g2_bytes(s, cts[i].first) == v["ct"][i]); CHECK(cts[i].second == v["msg_ct"][i]); }
+  std::vector<const Ciphertext*> refs;
+  for (auto& c : cts) refs.push_back(&c);
+  CHECK(vec_decrypt(proofs, refs) == v["messages"]);
+}
+
 int main(int argc, char** argv) {
   g_ptau = argc > 1 ? argv[1] : "tests/golden/ppot_0080_01_mini.ptau";
+  g_golden = argc > 2 ? argv[2] : "tests/golden/oracle_vectors.txt";
   RUN(test_fr_host_arithmetic);
   try {
     RUN(test_kzg_setup);
@@ -217,6 +277,7 @@ int main(int argc, char** argv) {
     RUN(test_vec_commit_encrypt_decrypt);
     RUN(test_laconic_ot);
     RUN(test_new_from_file_and_config1);
+    RUN(test_golden_vectors);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "unexpected exception: %s\n", e.what());
     return 1;

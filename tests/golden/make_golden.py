@@ -79,7 +79,22 @@ def main():
                  "ct_compressed": [bn.g2_serialize(c[0], True).hex() for c in cts],
                  "ct_uncompressed": [bn.g2_serialize(c[0], False).hex() for c in cts]},
     }
+    vec["wire"]["commitment_uncompressed"] = bn.g1_serialize(com, False).hex()
     json.dump(vec, open(os.path.join(HERE, "oracle_vectors.json"), "w"), indent=1)
+    # the same vectors as a line-based fixture for the C++ host-layer test (tests/cpp): `key hex [hex ...]`, scalars as
+    # 32-byte little-endian canonical integers, points as their ark-serialize uncompressed bytes
+    le = lambda x: int(x).to_bytes(32, "little").hex()
+    with open(os.path.join(HERE, "oracle_vectors.txt"), "w") as f:
+        f.write("tau " + le(tau) + "\n")
+        f.write("coeffs " + " ".join(le(c) for c in p) + "\n")
+        f.write("points " + " ".join(le(z) for z in points) + "\n")
+        f.write("values " + " ".join(le(v) for v in values) + "\n")
+        f.write("r " + " ".join(le(r) for r in rs) + "\n")
+        f.write("messages " + " ".join(m.hex() or "-" for m in msgs) + "\n")
+        f.write("commitment " + vec["wire"]["commitment_uncompressed"] + "\n")
+        f.write("proofs " + " ".join(vec["wire"]["proofs_uncompressed"]) + "\n")
+        f.write("ct " + " ".join(vec["wire"]["ct_uncompressed"]) + "\n")
+        f.write("msg_ct " + " ".join(c[1].hex() or "-" for c in cts) + "\n")
     print("golden fixtures written to", HERE)
 
 

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CPP = os.path.join(ROOT, "tests", "cpp")
 BIN = os.path.join(CPP, "_build", "test_keaki_host")
 PTAU = os.path.join(ROOT, "tests", "golden", "ppot_0080_01_mini.ptau")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "oracle_vectors.txt")
 
 
 def _build():
@@ -19,7 +20,7 @@ def _build():
 
 
 def _run():
-    return subprocess.run([BIN, PTAU], capture_output=True, text=True, timeout=900)
+    return subprocess.run([BIN, PTAU, GOLDEN], capture_output=True, text=True, timeout=900)
 
 
 def test_cpp_host_layer_builds_and_fails_loudly_without_gpu():
