@@ -1,4 +1,4 @@
-"""Small pass over every entry point for compute-sanitizer (memcheck / racecheck / synccheck): MSM at three window widths
+"""Small pass over every entry point for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): MSM at three window widths
 (two-digit reduction, quad-cooperative tail), open-all, encrypt (both per-commitment tables), decrypt on the pairing VM,
 verify, wire format."""
 import sys
