@@ -263,7 +263,9 @@ static void msm_run(kb_ctx* ctx, const uint32_t* scalars, bool from_host, uint64
     launch_msm_reduce(ctx, buckets, nb, d_out_xy, d_out_inf);
     return;
   }
-  const uint64_t na = n / 4, nbp = n - na;
+  uint64_t na = n / 4;
+  if (const char* e = getenv("KB_MSM_FIRST_DIV")) { int d = atoi(e); if (d >= 2 && d <= 64) na = n / d; }   // tuning override
+  const uint64_t nbp = n - na;
   MsmSort wa(ctx, nb, na, tab.nwin), wb(ctx, nb, nbp, tab.nwin);
   cudaStream_t side = ctx->copy_stream;
   try {
