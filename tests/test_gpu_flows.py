@@ -264,13 +264,12 @@ def test_full_size_we_roundtrip_65536(ctx):
 
 # ------------------------------------------------------------------ BASELINE config 5: laconic OT at scale
 def test_config5_laconic_ot_full_flow_at_scale(ctx):
-    """tests/laconic_ot.rs flow with 2^k - 1 receiver bits on one GPU (k = 16 by default, KB_OT_LOG_N=20 for the
-    BASELINE size): vec_commit with open_fk at d = 2^k, 2 x (2^k - 1) encryptions, 2^k - 1
+    """tests/laconic_ot.rs flow with 2^k - 1 receiver bits on one GPU (k = 20, the BASELINE size; KB_OT_LOG_N overrides): vec_commit with open_fk at d = 2^k, 2 x (2^k - 1) encryptions, 2^k - 1
     decryptions; all indices round-trip, the other message set does not decrypt, and commitment / proofs /
     ciphertexts agree with the trapdoor and the C oracle on samples."""
     from oracle import coracle as co
     from tests import ot_flow
-    k = int(os.environ.get("KB_OT_LOG_N", "16"))
+    k = int(os.environ.get("KB_OT_LOG_N", "20"))
     res = ot_flow.run(ctx, k, checker=(bn, co, L))
     print(json.dumps(res))
     assert res["roundtrip_all_indices"] and res["other_set_fails"]
