@@ -279,3 +279,14 @@ def test_encrypt_decrypt_roundtrip_larger(ctx, srs):
     ct, ct_inf, msg_ct = ctx.encrypt_batch(com_xy, com_inf, L.fr_vec(points).reshape(n, 8), Pe, rs, msgs, off)
     out = ctx.decrypt_batch(proofs, pinf, ct, ct_inf, msg_ct, off)
     assert np.array_equal(out[: 32 * n], msgs)
+
+
+def test_msm_skewed_scalars_one_bucket_per_window(ctx, srs):
+    """every scalar equal: each window puts all its entries into ONE bucket (the worst case for the one-thread-per-bucket
+    accumulation and for the size-ordered schedule); commit(k, k, ..., k) = k * sum_i [tau^i]_1 = k (tau^n - 1)/(tau - 1) G1"""
+    n = 1 << 13   # the fixture's SRS length
+    for k in (bn.R - 1, 0x0FEDCBA987654321FEDCBA987654321FEDCBA987654321FEDCBA98765432 % bn.R):
+        sc = np.tile(L.fr_m(k), (n, 1))
+        xy, inf = ctx.msm_g1(np.ascontiguousarray(sc), n=n)
+        want = bn.g1_mul(bn.G1_GEN, k * (pow(TAU, n, bn.R) - 1) * pow(TAU - 1, -1, bn.R) % bn.R)
+        assert (None if inf else L.g1_from(xy)) == want

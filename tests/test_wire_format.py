@@ -119,6 +119,14 @@ def test_gpu_wire_format_rejects_what_the_oracle_rejects(ctx):
     assert ok[0] == 0
     xy, _, ok = ctx.g1_deserialize(np.frombuffer(off, np.uint8).reshape(1, 64), False, False)
     assert ok[0] == 1 and L.g1_from(xy[0]) == (1, 3)
+    # uncompressed with a non-canonical y (y = q), and with stray flag bits in the x bytes: InvalidData in arkworks
+    bad_y = (1).to_bytes(32, "little") + bn.Q.to_bytes(32, "little")
+    stray = bytearray(bn.g1_serialize(bn.G1_GEN, False)); stray[31] |= 0x80
+    for blob in (bad_y, bytes(stray)):
+        with pytest.raises(ValueError):
+            bn.g1_deserialize(blob, False)
+        _, inf, ok = ctx.g1_deserialize(np.frombuffer(blob, np.uint8).reshape(1, 64), False, True)
+        assert ok[0] == 0 and inf[0] == 1
     t = _twist_point_outside_g2()
     for c in (True, False):
         blob = np.frombuffer(bn.g2_serialize(t, c), np.uint8).reshape(1, -1)
