@@ -353,6 +353,8 @@ def run_ours(args):
                "e2e": {"value": we_e2e, "unit": "ops/s", "h2d_bytes_per_step": n_we * (136 + 234), "d2h_bytes_per_step": n_we * (161 + MSG_LEN)},
                "gpu_launches": launches_we,
                "kernels_ms": {"encrypt_kernel+encrypt_ct_kernel": enc_ms, "pairing_vm_kernel": dec_ms},
+               "config": {"workload": "batched witness encryption + decryption of 2^%d messages of %d B per GPU (BASELINE.json configs[3])" % (args.log_we, MSG_LEN),
+                          "l2": "inputs larger than L2 (fixed-base tables of 128-384 MiB are gathered at random per message; the VM scratch is %d MiB per launch)" % ((80 * 32 * 2 * n_we) >> 20)},
                "roofline": {"bound": "imad", "kernel": "pairing_vm_kernel+encrypt_kernel",
                             "achieved": (IMAD_PER_ENCRYPT + IMAD_PER_DECRYPT) * n_we / ((enc_ms + dec_ms) * 1e-3) / 1e12,
                             "peak": peaks["imad_per_s"] / 1e12, "unit": "TIMAD/s",
