@@ -8,6 +8,7 @@
 //   h = first d entries of DFT^-1_2d(hat_h) (unscaled); proofs = DFT_d(h)            (:194-200).
 // G1 transforms use XYZZ points and scalar-multiplication butterflies, skipping unit twiddles.
 #include "ctx.cuh"
+#include "quad.cuh"
 #include "consts_gen.cuh"
 
 namespace kb {
@@ -179,6 +180,28 @@ __global__ void __launch_bounds__(128) g1_butterfly_kernel(uint32_t* __restrict_
   st_g1x(a + 32 * (size_t)j, ec_add(u, neg(v)));
 }
 
+// The same butterfly with four lanes per butterfly (quad.cuh).  Small domains are latency-bound: a stage of a few
+// thousand butterflies waits for ONE scalar multiplication per thread (about 2,200 dependent products), so the quad's
+// shorter dependent chain matters and its extra lanes cost nothing.
+__global__ void __launch_bounds__(128) g1_butterfly4_kernel(uint32_t* __restrict__ a, const uint32_t* __restrict__ tw_canon, int logn, int s) {
+  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const QuadLane ql = quad_lane();
+  const uint32_t half_n = 1u << (logn - 1);
+  if (t >= half_n) return;   // whole quads leave together
+  const uint32_t half = 1u << s;
+  const uint32_t k = t & (half - 1), i = ((t >> s) << (s + 1)) + k, j = i + half;
+  G1 u = ld_g1x(a + 32 * (size_t)i);
+  G1 v = ld_g1x(a + 32 * (size_t)j);
+  if (k != 0 && !v.is_inf()) {
+    uint32_t kk[8];
+    const uint32_t* src = tw_canon + 8 * (size_t)(k << (logn - 1 - s));
+    for (int q = 0; q < 8; q++) kk[q] = src[q];
+    v = g1_mul_glv4(v, kk, ql);
+  }
+  const G1 r0 = g1_add4(u, v, ql), r1 = g1_add4(u, neg(v), ql);
+  if (ql.q == 0) { st_g1x(a + 32 * (size_t)i, r0); st_g1x(a + 32 * (size_t)j, r1); }
+}
+
 // in-place natural-order G1 transform on d_pts (XYZZ), unscaled
 static void g1_ntt_dev(kb_ctx* ctx, uint32_t* d_pts, int logn, bool inverse) {
   if (logn == 0) return;
@@ -186,7 +209,11 @@ static void g1_ntt_dev(kb_ctx* ctx, uint32_t* d_pts, int logn, bool inverse) {
   Twiddles tw(ctx, logn, inverse, true);
   DevBuf<uint32_t> tmp(ctx, 32 * n);
   KB_LAUNCH(ctx, g1_bitrev_kernel, cdiv(n, 256), 256, 0, d_pts, tmp.p, logn);
-  for (int s = 0; s < logn; s++) KB_LAUNCH(ctx, g1_butterfly_kernel, cdiv(n / 2, 128), 128, 0, tmp.p, tw.canon.p, logn, s);
+  const bool quads = n <= (1ull << 14);   // latency-bound sizes
+  for (int s = 0; s < logn; s++) {
+    if (quads) KB_LAUNCH(ctx, g1_butterfly4_kernel, cdiv(2 * n, 128), 128, 0, tmp.p, tw.canon.p, logn, s);
+    else KB_LAUNCH(ctx, g1_butterfly_kernel, cdiv(n / 2, 128), 128, 0, tmp.p, tw.canon.p, logn, s);
+  }
   KB_CUDA(cudaMemcpyAsync(d_pts, tmp.p, 128 * n, cudaMemcpyDeviceToDevice, ctx->stream));
 }
 
@@ -211,6 +238,15 @@ __global__ void __launch_bounds__(128) fk_pointwise_kernel(const uint32_t* __res
   if (i >= n2) return;
   Fr k = fp_from_mont<FrParams>(fp_load<FrParams>(hat_a + 8 * (size_t)i) * fp_load<FrParams>(inv2d));
   st_g1x(out + 32 * (size_t)i, g1_mul_glv(ld_g1x(hat_s + 32 * (size_t)i), k.v));
+}
+__global__ void __launch_bounds__(128) fk_pointwise4_kernel(const uint32_t* __restrict__ hat_s, const uint32_t* __restrict__ hat_a,
+                                                            const uint32_t* __restrict__ inv2d, uint32_t n2, uint32_t* __restrict__ out) {
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const QuadLane ql = quad_lane();
+  if (i >= n2) return;
+  Fr k = fp_from_mont<FrParams>(fp_load<FrParams>(hat_a + 8 * (size_t)i) * fp_load<FrParams>(inv2d));
+  const G1 r = g1_mul_glv4(ld_g1x(hat_s + 32 * (size_t)i), k.v, ql);
+  if (ql.q == 0) st_g1x(out + 32 * (size_t)i, r);
 }
 __global__ void __launch_bounds__(128) g1_xyzz_to_affine_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out_xy,
                                                                 uint8_t* __restrict__ out_inf) {
@@ -245,7 +281,8 @@ void open_all_fk(kb_ctx* ctx, const uint32_t* d_coeffs, uint64_t d, uint32_t* d_
   KB_LAUNCH(ctx, fk_build_a_kernel, cdiv(n2, 256), 256, 0, d_coeffs, (uint32_t)d, a.p);
   fr_ntt_dev(ctx, a.p, logd + 1, false, false);
   Twiddles tw(ctx, logd + 1, true, false);  // only for (2d)^-1 at tw[d]
-  KB_LAUNCH(ctx, fk_pointwise_kernel, cdiv(n2, 128), 128, 0, hat_s, a.p, tw.tw.p + 8 * (size_t)d, n2, h.p);
+  if (n2 <= (1u << 14)) KB_LAUNCH(ctx, fk_pointwise4_kernel, cdiv(4ull * n2, 128), 128, 0, hat_s, a.p, tw.tw.p + 8 * (size_t)d, n2, h.p);
+  else KB_LAUNCH(ctx, fk_pointwise_kernel, cdiv(n2, 128), 128, 0, hat_s, a.p, tw.tw.p + 8 * (size_t)d, n2, h.p);
   g1_ntt_dev(ctx, h.p, logd + 1, true);
   g1_ntt_dev(ctx, h.p, logd, false);  // first d entries (src/kzg.rs:197-200)
   KB_LAUNCH(ctx, g1_xyzz_to_affine_kernel, cdiv(d, 128), 128, 0, h.p, (uint32_t)d, d_proofs, d_inf);
