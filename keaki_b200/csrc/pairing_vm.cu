@@ -37,6 +37,10 @@ struct DevLane {
     const uint4* p = sm + (size_t)s * 2 * VM_BLOCK + (t ? -1 : 1);
     return unpack(p[0], p[VM_BLOCK]);
   }
+  __device__ __forceinline__ Fq ld_c(uint32_t s, uint32_t h) const {   // coordinate h of the slot, whichever lane asks
+    const uint4* p = sm + (size_t)s * 2 * VM_BLOCK + ((int)h - (int)t);
+    return unpack(p[0], p[VM_BLOCK]);
+  }
   __device__ __forceinline__ void st(uint32_t s, const Fq& a) const {
     uint4* p = sm + (size_t)s * 2 * VM_BLOCK;
     p[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);

@@ -171,6 +171,7 @@ struct HostLane {
   uint32_t t;
   Fq ld(uint32_t i) const { return sh->s[t][i]; }
   Fq ld_partner(uint32_t i) const { return sh->s[1 - t][i]; }
+  Fq ld_c(uint32_t i, uint32_t h) const { return sh->s[h][i]; }
   void st(uint32_t i, const Fq& v) { sh->s[t][i] = v; }
   Fq ldg(uint32_t i) const { return sh->g[t][i]; }
   void stg(uint32_t i, const Fq& v) { sh->g[t][i] = v; }
