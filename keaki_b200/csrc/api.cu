@@ -73,6 +73,8 @@ int32_t kb_ctx_create(int32_t device, kb_ctx** out) {
     wire_upload_consts();
     we_init_tables(ctx);
     vm_init(ctx);
+    st_init(ctx);
+    if (const char* e = getenv("KB_PAIRING_IMPL")) ctx->pairing_impl = (e[0] == 'v') ? 0 : 1;   // tuning override
     KB_CUDA(cudaStreamSynchronize(ctx->stream));
   } catch (const std::exception& e) {
     fprintf(stderr, "kb_ctx_create: %s\n", e.what());
@@ -92,6 +94,7 @@ void kb_ctx_destroy(kb_ctx* ctx) {
   fk_free(ctx);
   we_free(ctx);
   vm_free(ctx);
+  st_free(ctx);
   if (ctx->d_srs) cudaFree(ctx->d_srs);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->ev_copy) if (e) cudaEventDestroy(e);

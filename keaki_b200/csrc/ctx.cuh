@@ -62,6 +62,10 @@ struct kb_ctx {
   uint32_t* d_vm_consts = nullptr;
   int vm_slots = 0, vm_gslots = 0, vm_block = 128, vm_minb = 2;
   uint64_t vm_out = 0;               // the six output slots, one byte each
+  // compiled single-thread pairing (pairing_st.cu): Frobenius / twist constants; which kernel the batched paths use
+  uint32_t* d_st_consts = nullptr;
+  int st_shape = 0;
+  int pairing_impl = 1;              // 0 = pairing VM (two lanes + interpreter), 1 = compiled single-thread kernel; KB_PAIRING_IMPL=vm|st
 
   // FK open-all cache: hat_s = DFT_2d(reversed SRS prefix) per d
   struct FkCache { uint64_t d = 0; uint32_t* d_hat_s = nullptr; };
@@ -185,6 +189,10 @@ void we_free(kb_ctx* ctx);
 void we_upload_consts();
 void vm_init(kb_ctx* ctx);                             // pairing VM program upload (ctx creation)
 void vm_free(kb_ctx* ctx);
+void st_init(kb_ctx* ctx);                             // compiled pairing: constants upload (ctx creation)
+void st_free(kb_ctx* ctx);
+void st_pairing_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf, uint64_t n,
+                       int mode, uint32_t* d_gt, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out);
 void pairing_batch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
                    uint64_t n, uint8_t* d_gt_bytes);
 void decrypt_batch(kb_ctx* ctx, const uint32_t* d_proofs, const uint8_t* d_pinf, const uint32_t* d_ct, const uint8_t* d_cinf,

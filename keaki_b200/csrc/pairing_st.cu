@@ -1,0 +1,149 @@
+// Batched pairing / decapsulation kernel on the compiled single-thread pairing (pairing_st.cuh).
+// `decapsulate` (src/kem.rs:55-72) + the XOR of `decrypt` (src/enc.rs:44-55) over the batch of `vec_decrypt`
+// (src/vec.rs:72-81), and raw `E::pairing` (src/kem.rs:30,58; src/kzg.rs:148).
+//
+// One thread per pairing.  F and S (12 Fq2 slots) in shared memory as [slot][quarter][thread] uint4, so every
+// access of a warp is 512 contiguous bytes; the G2 accumulator, P, Q and the saved Fq12 values of the final
+// exponentiation in a per-thread global scratch with the same layout.  The kernel is persistent: a warp takes 32
+// pairings at a time from a global counter, so the scratch is sized by the resident threads and the tail of the
+// batch spreads over all SMs.  GT never leaves the chip on the decrypt path: canonical bytes -> BLAKE3 XOF -> XOR
+// happen in the epilogue.
+#include "ctx.cuh"
+#include "blake3.cuh"
+#include "pairing_st.cuh"
+#include "consts_gen.cuh"
+#include <cstdlib>
+
+namespace kb {
+
+extern __shared__ uint4 st_smem[];
+
+template <int BLOCK>
+struct StDevMem {
+  uint4* gl;          // scratch, already offset by the global thread index
+  uint32_t gstride;   // threads in the launch
+
+  __device__ __forceinline__ static Fq2 unpack(const uint4& q0, const uint4& q1, const uint4& q2, const uint4& q3) {
+    Fq2 r;
+    r.c0.v[0] = q0.x; r.c0.v[1] = q0.y; r.c0.v[2] = q0.z; r.c0.v[3] = q0.w;
+    r.c0.v[4] = q1.x; r.c0.v[5] = q1.y; r.c0.v[6] = q1.z; r.c0.v[7] = q1.w;
+    r.c1.v[0] = q2.x; r.c1.v[1] = q2.y; r.c1.v[2] = q2.z; r.c1.v[3] = q2.w;
+    r.c1.v[4] = q3.x; r.c1.v[5] = q3.y; r.c1.v[6] = q3.z; r.c1.v[7] = q3.w;
+    return r;
+  }
+  __device__ __forceinline__ Fq2 ld(int a) const {
+    if (a < 16) {
+      const uint4* p = st_smem + (size_t)(4 * a) * BLOCK + threadIdx.x;
+      return unpack(p[0], p[BLOCK], p[2 * BLOCK], p[3 * BLOCK]);
+    }
+    const uint4* p = gl + (size_t)(4 * (a - 16)) * gstride;
+    return unpack(p[0], p[gstride], p[2 * (size_t)gstride], p[3 * (size_t)gstride]);
+  }
+  __device__ __forceinline__ void st(int a, const Fq2& x) const {
+    const uint4 q0 = make_uint4(x.c0.v[0], x.c0.v[1], x.c0.v[2], x.c0.v[3]), q1 = make_uint4(x.c0.v[4], x.c0.v[5], x.c0.v[6], x.c0.v[7]);
+    const uint4 q2 = make_uint4(x.c1.v[0], x.c1.v[1], x.c1.v[2], x.c1.v[3]), q3 = make_uint4(x.c1.v[4], x.c1.v[5], x.c1.v[6], x.c1.v[7]);
+    if (a < 16) {
+      uint4* p = st_smem + (size_t)(4 * a) * BLOCK + threadIdx.x;
+      p[0] = q0; p[BLOCK] = q1; p[2 * BLOCK] = q2; p[3 * BLOCK] = q3;
+    } else {
+      uint4* p = gl + (size_t)(4 * (a - 16)) * gstride;
+      p[0] = q0; p[gstride] = q1; p[2 * (size_t)gstride] = q2; p[3 * (size_t)gstride] = q3;
+    }
+  }
+};
+
+// consts: FROB_GAMMA (18 x 16 limbs) || TW_X || TW_Y
+// mode 0: write the 96 canonical GT words; mode 1: key = BLAKE3-XOF(GT bytes), out = key XOR msg_ct.
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) pairing_st_kernel(const uint32_t* __restrict__ consts, const uint32_t* __restrict__ g1,
+                                                                 const uint8_t* __restrict__ g1_inf, const uint32_t* __restrict__ g2,
+                                                                 const uint8_t* __restrict__ g2_inf, uint64_t n, uint4* __restrict__ scratch,
+                                                                 unsigned long long* __restrict__ counter, int mode, uint32_t* __restrict__ gt_out,
+                                                                 const uint8_t* __restrict__ msg_ct, const uint64_t* __restrict__ off,
+                                                                 uint8_t* __restrict__ out) {
+  StDevMem<BLOCK> m;
+  m.gstride = gridDim.x * BLOCK;
+  m.gl = scratch + (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    const uint64_t i = base + lane;
+    const bool live = i < n;
+    const uint64_t j = live ? i : n - 1;   // padding lanes recompute the last pairing
+    Fq2 P, qx, qy;
+    P.c0 = fp_load<FqParams>(g1 + 16 * j); P.c1 = fp_load<FqParams>(g1 + 16 * j + 8);
+    qx.c0 = fp_load<FqParams>(g2 + 32 * j); qx.c1 = fp_load<FqParams>(g2 + 32 * j + 8);
+    qy.c0 = fp_load<FqParams>(g2 + 32 * j + 16); qy.c1 = fp_load<FqParams>(g2 + 32 * j + 24);
+    const bool trivial = (g1_inf && g1_inf[j]) || (g2_inf && g2_inf[j]) || P.is_zero() || (qx.is_zero() && qy.is_zero());
+    m.st(st::G_P, P); m.st(st::G_QX, qx); m.st(st::G_QY, qy);
+    st::miller(m, consts + 18 * 16);
+    st::final_exp(m, consts);
+    uint32_t w[96];
+    st::gt_words(m, w);
+    if (trivial) {   // arkworks skips pairs with an infinity: GT = 1
+#pragma unroll
+      for (int k = 0; k < 96; k++) w[k] = k == 0 ? 1u : 0u;
+    }
+    if (!live) continue;
+    if (mode == 0) {
+      uint4* o = reinterpret_cast<uint4*>(gt_out + 96 * i);
+#pragma unroll
+      for (int k = 0; k < 24; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    } else {
+      const uint64_t lo = off[i], hi = off[i + 1];
+      b3_gt_xof_xor(w, msg_ct + lo, out + lo, hi - lo);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static constexpr int ST_SMEM_PER_THREAD = 12 * 64;
+
+template <int BLOCK, int MINB>
+static void st_go(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf, uint64_t n, int mode,
+                  uint32_t* d_gt, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out) {
+  static bool prepared = false;
+  const int smem = BLOCK * ST_SMEM_PER_THREAD;
+  if (!prepared) {
+    KB_CUDA(cudaFuncSetAttribute(pairing_st_kernel<BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    prepared = true;
+  }
+  unsigned blocks = (unsigned)ctx->sm_count * MINB;
+  const unsigned need = cdiv(n, 32) * 32 / BLOCK + 1;   // never more threads than (padded) pairings
+  if (blocks > need) blocks = need;
+  const size_t threads = (size_t)blocks * BLOCK;
+  DevBuf<uint4> scratch(ctx, (size_t)st::SCRATCH_SLOTS * 4 * threads);
+  DevBuf<unsigned long long> counter(ctx, 1);
+  KB_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), ctx->stream));
+  timer_start(ctx, KB_T_PAIRING);
+  KB_LAUNCH(ctx, (pairing_st_kernel<BLOCK, MINB>), blocks, BLOCK, smem, ctx->d_st_consts, d_g1, d_g1_inf, d_g2, d_g2_inf, n, scratch.p, counter.p,
+            mode, d_gt, d_msg_ct, d_off, d_out);
+  timer_stop(ctx, KB_T_PAIRING);
+}
+
+void st_init(kb_ctx* ctx) {
+  KB_CUDA(cudaMalloc((void**)&ctx->d_st_consts, (18 + 2) * 64));
+  KB_CUDA(cudaMemcpyAsync(ctx->d_st_consts, consts::FROB_GAMMA, 18 * 64, cudaMemcpyHostToDevice, ctx->stream));
+  KB_CUDA(cudaMemcpyAsync(ctx->d_st_consts + 18 * 16, consts::TW_X, 64, cudaMemcpyHostToDevice, ctx->stream));
+  KB_CUDA(cudaMemcpyAsync(ctx->d_st_consts + 19 * 16, consts::TW_Y, 64, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->st_shape = 0;
+  if (const char* e = getenv("KB_PAIRING_ST_SHAPE")) ctx->st_shape = atoi(e);   // tuning override
+}
+void st_free(kb_ctx* ctx) { cudaFree(ctx->d_st_consts); ctx->d_st_consts = nullptr; }
+
+void st_pairing_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf, uint64_t n,
+                       int mode, uint32_t* d_gt, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out) {
+  switch (ctx->st_shape) {
+    case 1: st_go<64, 4>(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out); break;
+    case 2: st_go<96, 3>(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out); break;
+    case 3: st_go<128, 1>(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out); break;
+    default: st_go<128, 2>(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out); break;
+  }
+}
+
+}  // namespace kb

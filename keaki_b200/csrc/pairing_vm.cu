@@ -212,12 +212,14 @@ static void vm_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf
 void pairing_batch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
                    uint64_t n, uint8_t* d_gt_bytes) {
   if (!n) return;
+  if (ctx->pairing_impl == 1) return st_pairing_launch(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, 0, reinterpret_cast<uint32_t*>(d_gt_bytes), nullptr, nullptr, nullptr);
   vm_launch(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, 0, reinterpret_cast<uint32_t*>(d_gt_bytes), nullptr, nullptr, nullptr);
 }
 
 void decrypt_batch(kb_ctx* ctx, const uint32_t* d_proofs, const uint8_t* d_pinf, const uint32_t* d_ct, const uint8_t* d_cinf,
                    const uint8_t* d_msg_ct, const uint64_t* d_off, uint64_t n, uint8_t* d_out) {
   if (!n) return;
+  if (ctx->pairing_impl == 1) return st_pairing_launch(ctx, d_proofs, d_pinf, d_ct, d_cinf, n, 1, nullptr, d_msg_ct, d_off, d_out);
   vm_launch(ctx, d_proofs, d_pinf, d_ct, d_cinf, n, 1, nullptr, d_msg_ct, d_off, d_out);
 }
 

@@ -16,6 +16,7 @@
 #include "../../keaki_b200/csrc/msm_digits.cuh"
 #include "../../keaki_b200/csrc/pairing_vm.cuh"
 #include "../../keaki_b200/csrc/pairing_prog_gen.cuh"
+#include "../../keaki_b200/csrc/pairing_st.cuh"
 
 using namespace kb;
 
@@ -223,6 +224,54 @@ void he_mul9_add(const uint32_t* x, const uint32_t* y, uint32_t* out) { stq(out,
 // signed-digit recoding used by the MSM (window c bits): digits[w] in [-2^(c-1), 2^(c-1)]
 void he_msm_digits(const uint32_t* scalar_canonical, int c, int nwin, int32_t* digits) {
   msm_signed_digits(scalar_canonical, c, nwin, digits);
+}
+
+}  // extern "C"
+
+// The compiled single-thread pairing (pairing_st.cuh) on a host slot store: GT as 384 canonical bytes.
+struct StState { Fq2 on[16]; Fq2 sc[st::SCRATCH_SLOTS]; };
+struct StMem {
+  StState* p;
+  Fq2 ld(int a) const { return a < 16 ? p->on[a] : p->sc[a - 16]; }
+  void st(int a, const Fq2& v) const { if (a < 16) p->on[a] = v; else p->sc[a - 16] = v; }
+};
+
+extern "C" {
+
+void he_st_pairing_bytes(const uint32_t* p_xy, const uint32_t* q_xy, uint8_t* out384) {
+  StState* s = new StState();
+  StMem m{s};
+  m.st(st::G_P, ldq2(p_xy));
+  m.st(st::G_QX, ldq2(q_xy));
+  m.st(st::G_QY, ldq2(q_xy + 16));
+  uint32_t tw[32];
+  memcpy(tw, consts::TW_X, 64); memcpy(tw + 16, consts::TW_Y, 64);
+  st::miller(m, tw);
+  st::final_exp(m, consts::FROB_GAMMA);
+  uint32_t w[96];
+  st::gt_words(m, w);
+  memcpy(out384, w, 384);
+  delete s;
+}
+// lazy-reduction pieces: op 0: out16 = mul_wide(a, b); op 1: out8 = redc(a16); op 2: out16 = fq2_mul_lazy(a16, b16)
+void he_lazy_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  if (op == 0) { lz::W t = lz::mul_wide(ldq(a), ldq(b)); memcpy(out, t.v, 64); }
+  else if (op == 1) { lz::W t; memcpy(t.v, a, 64); stq(out, lz::redc<FqParams>(t)); }
+  else stq2(out, lz::fq2_mul_lazy(ldq2(a), ldq2(b)));
+}
+// Fq12-level routines of pairing_st.cuh on F: op 0 F*B, 1 F*conj(B), 2 F^2, 3 cyclotomic F^2, 4 F * line(b[0..47]), 5..7 frobenius 1..3, 8 inverse
+void he_st_f12_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  StState* s = new StState();
+  StMem m{s};
+  for (int i = 0; i < 6; i++) m.st(st::F + i, ldq2(a + 16 * i));
+  if (op <= 1) { for (int i = 0; i < 6; i++) m.st(st::G12(0) + i, ldq2(b + 16 * i)); st::f12mul(m, st::G12(0), op); }
+  else if (op == 2) st::f12sqr(m);
+  else if (op == 3) st::cycsqr(m);
+  else if (op == 4) { for (int i = 0; i < 3; i++) m.st(st::S + i, ldq2(b + 16 * i)); st::f12mul_line(m); }
+  else if (op <= 7) st::f12frob(m, op - 4, consts::FROB_GAMMA);
+  else st::f12inv(m);
+  for (int i = 0; i < 6; i++) stq2(out + 16 * i, m.ld(st::F + i));
+  delete s;
 }
 
 }  // extern "C"
