@@ -13,9 +13,9 @@
  *  - Pointers may be host memory (pageable or pinned) or device memory of the context's GPU (e.g. a
  *    torch tensor's data_ptr); device buffers skip the PCIe copies.  Outputs follow the same rule.
  *  - Every call is blocking and returns 0 on success or a negative kb_status; nothing unwinds.
- *    `kb_last_error` gives a message.  One context = one GPU = one caller thread at a time;
- *    distinct contexts are independent (one process per GPU under torchrun, or several contexts in
- *    one process).
+ *    `kb_last_error` gives a message.  One context = one caller thread at a time; a context is one
+ *    GPU (kb_ctx_create) or several GPUs of one box (kb_ctx_create_multi); distinct contexts are
+ *    independent (one process per GPU under torchrun, or several contexts in one process).
  *  - There is NO CPU fallback: if no CUDA device is usable, kb_ctx_create fails.
  */
 #ifndef KEAKI_B200_H
@@ -35,7 +35,8 @@ typedef enum {
   KB_ERR_ARG = -2,             /* null pointer / bad size */
   KB_ERR_POLY_TOO_LARGE = -3,  /* KZGError::PolynomialTooLarge (src/kzg.rs:93-95, 205-209) */
   KB_ERR_NO_SRS = -4,          /* kb_srs_upload / kb_srs_generate not called yet */
-  KB_ERR_DOMAIN = -5           /* size not a power of two, or > 2^28 (src/kzg.rs:163 unwrap) */
+  KB_ERR_DOMAIN = -5,          /* size not a power of two, or > 2^28 (src/kzg.rs:163 unwrap) */
+  KB_ERR_INVALID_POINT = -6    /* kb_srs_validate: an SRS element is not a point of its group */
 } kb_status;
 
 /* Library version and the CUDA architecture the kernels were built for ("sm_100a"). */
@@ -44,6 +45,13 @@ const char* kb_version(void);
 /* Context on CUDA device `device`.  Replaces nothing in the reference (it has no device state);
  * owned by the shim's `KZGSetup` (src/kzg.rs:22-29). */
 int32_t kb_ctx_create(int32_t device, kb_ctx** out);
+/* One context over ndev GPUs of the box ("one process drives all 8 GPUs"), one host thread + stream per
+ * device.  Every device holds the SRS and its tables; kb_msm_g1 (`commit`, src/kzg.rs:89-101) then splits its call by
+ * point range - one partial sum per device, added on the first - and kb_encrypt_batch / kb_decrypt_batch (the loops of
+ * src/vec.rs:63-66,75-78) by index; kb_srs_upload / kb_srs_generate reach every device; all other entry points run on
+ * devices[0].  Same handle type and the same calls as a single-device context. */
+int32_t kb_ctx_create_multi(const int32_t* devices, int32_t ndev, kb_ctx** out);
+int32_t kb_ctx_device_count(const kb_ctx* ctx);
 void kb_ctx_destroy(kb_ctx* ctx);
 const char* kb_last_error(const kb_ctx* ctx);
 
@@ -61,6 +69,13 @@ int32_t kb_srs_generate(kb_ctx* ctx, const uint32_t* tau /* 8, Montgomery Fr */,
                         uint32_t* out_g1_xy /* n*16 or NULL */, uint32_t* out_tau_g2_xy /* 32 or NULL */);
 
 uint64_t kb_srs_len(const kb_ctx* ctx);
+
+/* Validation of the resident SRS on the GPU.  The reference reads the ptau sections with
+ * `deserialize_uncompressed_unchecked` (src/kzg/ptau.rs:266,314) and so accepts anything; a shim's `new_from_file` calls
+ * this after kb_srs_upload.  Every G1 power must be a finite point of y^2 = x^3 + 3 with coordinates below q (cofactor 1:
+ * on the curve = in the group); [tau]_2 a point of the twist with [r]P = O.  Returns KB_OK, or KB_ERR_INVALID_POINT with
+ * *first_bad (may be NULL) = the smallest failing G1 index, or kb_srs_len when only [tau]_2 fails. */
+int32_t kb_srs_validate(kb_ctx* ctx, uint64_t* first_bad);
 
 /* `commit` (src/kzg.rs:89-101) = VariableBaseMSM::msm_unchecked(&g1_aff[..n], scalars):
  * sum_{i<n} scalars[i] * g1[first + i].  `first` > 0 is used for point-range sharding across GPUs

@@ -164,9 +164,17 @@ inline void check(kb_ctx* c, int32_t rc, const char* what) {
   const char* m = kb_last_error(c);
   throw BackendError(std::string(what) + ": " + (m ? m : "error") + " (" + std::to_string(rc) + ")");
 }
-/// context for the calls of the reference that take no setup (`decapsulate`, `decrypt`, `vec_decrypt`, domains)
+/// context for the calls of the reference that take no setup (`decapsulate`, `decrypt`, `vec_decrypt`, domains): the
+/// context of the most recently created KZGSetup (same device, no second set of tables); one on device 0 is created
+/// only if no setup exists yet
+inline std::weak_ptr<kb_ctx>& latest_setup_ctx() { static std::weak_ptr<kb_ctx> w; return w; }
 inline CtxPtr& default_ctx_slot() { static CtxPtr c; return c; }
-inline kb_ctx* default_ctx() { if (!default_ctx_slot()) default_ctx_slot() = make_ctx(0); return default_ctx_slot().get(); }
+inline CtxPtr default_ctx_ptr() {
+  if (CtxPtr live = latest_setup_ctx().lock()) return live;
+  if (!default_ctx_slot()) default_ctx_slot() = make_ctx(0);
+  return default_ctx_slot();
+}
+inline kb_ctx* default_ctx() { return default_ctx_ptr().get(); }   // callers use it within one blocking call
 inline const uint32_t* u32(const Fr* p) { return reinterpret_cast<const uint32_t*>(p); }
 inline uint32_t* u32(Fr* p) { return reinterpret_cast<uint32_t*>(p); }
 static_assert(sizeof(Fr) == 32, "Fr must be 4 x u64");
@@ -211,22 +219,32 @@ inline void get_powers_from_file(const std::string& path, std::vector<G1>& g1, s
   auto rd32 = [&](size_t o) { uint32_t v; std::memcpy(&v, &data[o], 4); return v; };
   auto rd64 = [&](size_t o) { uint64_t v; std::memcpy(&v, &data[o], 8); return v; };
   if (data.size() < 12 || std::memcmp(data.data(), "ptau", 4) != 0) throw SetupFileError("InvalidFileType");
-  if (rd32(8) != 11) throw SetupFileError("InvalidSectionCount(" + std::to_string(rd32(8)) + ")");
+  if (rd32(8) != 11) throw SetupFileError("InvalidNumberOfSections(" + std::to_string(rd32(8)) + ")");
   size_t off = 12, sec_off[16] = {0}, sec_len[16] = {0};
+  bool sec_seen[16] = {false};
   for (int s = 0; s < 11; s++) {
     if (off + 12 > data.size()) throw SetupFileError("UnexpectedEof");
     uint32_t id = rd32(off); uint64_t len = rd64(off + 4);
     if (!((id >= 1 && id <= 7) || (id >= 12 && id <= 15))) throw SetupFileError("UnknownSection(" + std::to_string(id) + ")");
-    off += 12; sec_off[id] = off; sec_len[id] = len; off += len;
+    off += 12;
+    if (len > data.size() - off) throw SetupFileError("UnexpectedEof");
+    if (!sec_seen[id]) { sec_seen[id] = true; sec_off[id] = off; sec_len[id] = (size_t)len; }   // a repeated id keeps its first occurrence
+    off += (size_t)len;
   }
   if (off != data.size()) throw SetupFileError("SectionsNotContiguous");
+  // `FileSections::get` (src/kzg/ptau.rs:146-150): the three sections that are read must be present
+  for (int id = 1; id <= 3; id++) if (!sec_seen[id]) throw SetupFileError("EmptySection(" + std::to_string(id) + ")");
   size_t h = sec_off[1];
   static const uint8_t QMOD[32] = {0x47, 0xfd, 0x7c, 0xd8, 0x16, 0x8c, 0x20, 0x3c, 0x8d, 0xca, 0x71, 0x68, 0x91, 0x6a, 0x81, 0x97,
                                    0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
+  if (sec_len[1] < 44) throw SetupFileError("ParseError(header section too short)");
   if (rd32(h) != 32 || std::memcmp(&data[h + 4], QMOD, 32) != 0) throw SetupFileError("InvalidFieldModulus");
   uint32_t power = rd32(h + 36);
+  if (power > 28) throw SetupFileError("ParseError(power " + std::to_string(power) + " > 28)");   // 2-adicity of Fr; keeps the sizes below in range
   size_t n1 = 2 * (size_t(1) << power) - 1, n2 = size_t(1) << power;
-  if (sec_len[2] < n1 * 64 || sec_len[3] < n2 * 128) throw SetupFileError("SectionTooShort");
+  // src/kzg/ptau.rs:251-256, 299-304: exact section sizes
+  if (sec_len[2] != n1 * 64) throw SetupFileError("ElementSizeMismatch(" + std::to_string(n1 * 64) + ", " + std::to_string(sec_len[2]) + ")");
+  if (sec_len[3] != n2 * 128) throw SetupFileError("ElementSizeMismatch(" + std::to_string(n2 * 128) + ", " + std::to_string(sec_len[3]) + ")");
   g1.resize(n1); g2.resize(n2);
   for (size_t i = 0; i < n1; i++) { std::memcpy(g1[i].xy, &data[sec_off[2] + 64 * i], 64); g1[i].inf = false; }
   for (size_t i = 0; i < n2; i++) { std::memcpy(g2[i].xy, &data[sec_off[3] + 128 * i], 128); g2[i].inf = false; }
@@ -239,7 +257,7 @@ inline void get_powers_from_file(const std::string& path, std::vector<G1>& g1, s
 class KZGSetup {
  public:
   /// src/kzg.rs:33-52
-  static KZGSetup new_from_file(const std::string& file, int device = 0) {
+  static KZGSetup new_from_file(const std::string& file, int device = 0, bool validate = true) {
     std::vector<G1> g1; std::vector<G2> g2;
     ptau::get_powers_from_file(file, g1, g2);
     if (g2.size() < 2) throw SetupFileError("EmptySection(3)");
@@ -248,7 +266,15 @@ class KZGSetup {
     std::vector<uint32_t> flat(16 * g1.size());
     for (size_t i = 0; i < g1.size(); i++) std::memcpy(&flat[16 * i], g1[i].xy, 64);
     detail::check(s.ctx_.get(), kb_srs_upload(s.ctx_.get(), flat.data(), g1.size(), g2[1].xy), "kb_srs_upload");
+    // unlike the reference (`deserialize_uncompressed_unchecked`, src/kzg/ptau.rs:266,314) the points are validated (on the GPU)
+    if (validate) {
+      uint64_t bad = 0;
+      int32_t rc = kb_srs_validate(s.ctx_.get(), &bad);
+      if (rc == KB_ERR_INVALID_POINT) throw SetupFileError(std::string("ParseError(") + kb_last_error(s.ctx_.get()) + ")");
+      detail::check(s.ctx_.get(), rc, "kb_srs_validate");
+    }
     s.g1_ = std::move(g1); s.tau_g2_ = g2[1];
+    detail::latest_setup_ctx() = s.ctx_;
     return s;
   }
   /// src/kzg.rs:55-70 ("Don't use this"): g1_pow[i] = tau^i G1, tau_g2 = tau G2, generated on the device
@@ -260,6 +286,7 @@ class KZGSetup {
     detail::check(s.ctx_.get(), kb_srs_generate(s.ctx_.get(), detail::u32(&secret), 0, max_d, flat.data(), s.tau_g2_.xy), "kb_srs_generate");
     s.g1_.resize(max_d);
     for (size_t i = 0; i < max_d; i++) { std::memcpy(s.g1_[i].xy, &flat[16 * i], 64); s.g1_[i].inf = false; }
+    detail::latest_setup_ctx() = s.ctx_;
     return s;
   }
   const std::vector<G1>& g1_pow() const { return g1_; }

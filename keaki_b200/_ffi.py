@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libkeaki_b200.so")
 
-KB_OK, KB_ERR_CUDA, KB_ERR_ARG, KB_ERR_POLY_TOO_LARGE, KB_ERR_NO_SRS, KB_ERR_DOMAIN = 0, -1, -2, -3, -4, -5
+KB_OK, KB_ERR_CUDA, KB_ERR_ARG, KB_ERR_POLY_TOO_LARGE, KB_ERR_NO_SRS, KB_ERR_DOMAIN, KB_ERR_INVALID_POINT = 0, -1, -2, -3, -4, -5, -6
 
 _vp, _u64, _i32, _u8 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32, ctypes.c_uint8
 
@@ -21,11 +21,14 @@ _vp, _u64, _i32, _u8 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32, ctypes.
 SIGNATURES = {
     "kb_version": (ctypes.c_char_p, []),
     "kb_ctx_create": (_i32, [_i32, ctypes.POINTER(_vp)]),
+    "kb_ctx_create_multi": (_i32, [ctypes.POINTER(_i32), _i32, ctypes.POINTER(_vp)]),
+    "kb_ctx_device_count": (_i32, [_vp]),
     "kb_ctx_destroy": (None, [_vp]),
     "kb_last_error": (ctypes.c_char_p, [_vp]),
     "kb_srs_upload": (_i32, [_vp, _vp, _u64, _vp]),
     "kb_srs_generate": (_i32, [_vp, _vp, _u64, _u64, _vp, _vp]),
     "kb_srs_len": (_u64, [_vp]),
+    "kb_srs_validate": (_i32, [_vp, ctypes.POINTER(_u64)]),
     "kb_msm_g1": (_i32, [_vp, _vp, _u64, _u64, _vp, _vp]),
     "kb_g1_mul_gen_batch": (_i32, [_vp, _vp, _u64, _vp, _vp]),
     "kb_g1_sum": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),
@@ -54,6 +57,10 @@ class KeakiB200Error(RuntimeError):
 
 class PolynomialTooLarge(KeakiB200Error):
     """KZGError::PolynomialTooLarge(len, max) — src/kzg.rs:205-209."""
+
+
+class InvalidSrsPoint(KeakiB200Error):
+    """kb_srs_validate found an SRS element that is not a point of its group (`.index`: G1 power, or srs_len for [tau]_2)."""
 
 
 _lib = None
@@ -95,14 +102,23 @@ def _u32(a):
 class Context:
     """One GPU.  Mirrors the C ABI one-to-one; higher layers (kzg/kem/enc/vec) build on it."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: an index, or a sequence of indices for ONE context over several GPUs of the box (kb_ctx_create_multi:
+        commit splits by point range, encrypt / decrypt batches by index, inside the library)."""
         self.lib = load_library()
         h = _vp()
-        rc = self.lib.kb_ctx_create(int(device), ctypes.byref(h))
+        if isinstance(device, (list, tuple)):
+            devs = (_i32 * len(device))(*[int(d) for d in device])
+            rc = self.lib.kb_ctx_create_multi(devs, len(device), ctypes.byref(h))
+        else:
+            rc = self.lib.kb_ctx_create(int(device), ctypes.byref(h))
         if rc != KB_OK:
             raise KeakiB200Error(rc, f"kb_ctx_create(device={device}) failed: no usable sm_100 GPU (there is no CPU fallback)")
         self.h = h
         self.device = device
+
+    def device_count(self):
+        return int(self.lib.kb_ctx_device_count(self.h))
 
     def close(self):
         if getattr(self, "h", None):
@@ -134,6 +150,16 @@ class Context:
         t2 = np.zeros(32, np.uint32)
         self._check(self.lib.kb_srs_generate(self.h, _ptr(_u32(tau_limbs)), first_power, n, _ptr(g1), _ptr(t2)))
         return g1, t2
+
+    def srs_validate(self):
+        """kb_srs_validate: raises InvalidSrsPoint (with .index) unless every resident SRS element is a point of its group."""
+        bad = _u64(0)
+        rc = self.lib.kb_srs_validate(self.h, ctypes.byref(bad))
+        if rc == KB_ERR_INVALID_POINT:
+            e = InvalidSrsPoint(rc, self.lib.kb_last_error(self.h).decode())
+            e.index = int(bad.value)
+            raise e
+        self._check(rc)
 
     def srs_len(self):
         return int(self.lib.kb_srs_len(self.h))

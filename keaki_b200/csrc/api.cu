@@ -3,6 +3,7 @@
 // CPU fallback anywhere behind these entry points.
 #include "ctx.cuh"
 #include <cstdlib>
+#include <thread>
 
 using namespace kb;
 
@@ -88,6 +89,8 @@ int32_t kb_ctx_create(int32_t device, kb_ctx** out) {
 
 void kb_ctx_destroy(kb_ctx* ctx) {
   if (!ctx) return;
+  for (kb_ctx* p : ctx->peers) kb_ctx_destroy(p);
+  ctx->peers.clear();
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   msm_free_tables(ctx);
@@ -104,11 +107,17 @@ void kb_ctx_destroy(kb_ctx* ctx) {
 }
 
 const char* kb_last_error(const kb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-uint64_t kb_launch_count(const kb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t kb_launch_count(const kb_ctx* ctx) {
+  if (!ctx) return 0;
+  uint64_t n = ctx->launches;
+  for (const kb_ctx* p : ctx->peers) n += p->launches;
+  return n;
+}
+int32_t kb_ctx_device_count(const kb_ctx* ctx) { return ctx ? 1 + (int32_t)ctx->peers.size() : 0; }
 float kb_last_kernel_ms(const kb_ctx* ctx, int32_t which) { return (ctx && which >= 0 && which < KB_T_COUNT) ? ctx->last_ms[which] : -1.f; }
 uint64_t kb_srs_len(const kb_ctx* ctx) { return ctx ? ctx->srs_n : 0; }
 
-int32_t kb_srs_upload(kb_ctx* ctx, const uint32_t* g1_aff_xy, uint64_t n, const uint32_t* tau_g2_xy) {
+static int32_t single_srs_upload(kb_ctx* ctx, const uint32_t* g1_aff_xy, uint64_t n, const uint32_t* tau_g2_xy) {
   KB_API_BEGIN(ctx)
   need(tau_g2_xy != nullptr && (n == 0 || g1_aff_xy != nullptr), "kb_srs_upload: null pointer");
   if (ctx->d_srs) { KB_CUDA(cudaFree(ctx->d_srs)); ctx->d_srs = nullptr; }
@@ -122,7 +131,7 @@ int32_t kb_srs_upload(kb_ctx* ctx, const uint32_t* g1_aff_xy, uint64_t n, const 
   KB_API_END(ctx)
 }
 
-int32_t kb_srs_generate(kb_ctx* ctx, const uint32_t* tau, uint64_t first_power, uint64_t n, uint32_t* out_g1_xy, uint32_t* out_tau_g2_xy) {
+static int32_t single_srs_generate(kb_ctx* ctx, const uint32_t* tau, uint64_t first_power, uint64_t n, uint32_t* out_g1_xy, uint32_t* out_tau_g2_xy) {
   KB_API_BEGIN(ctx)
   need(tau != nullptr, "kb_srs_generate: null tau");
   fk_free(ctx);
@@ -135,7 +144,22 @@ int32_t kb_srs_generate(kb_ctx* ctx, const uint32_t* tau, uint64_t first_power, 
   KB_API_END(ctx)
 }
 
-int32_t kb_msm_g1(kb_ctx* ctx, const uint32_t* scalars, uint64_t first, uint64_t n, uint32_t out_xy[16], uint8_t* out_inf) {
+int32_t kb_srs_validate(kb_ctx* ctx, uint64_t* first_bad) {
+  unsigned long long bad = ~0ull;
+  KB_API_BEGIN(ctx)
+  need_srs(ctx);
+  DevBuf<unsigned long long> d_bad(ctx, 1);
+  srs_validate(ctx, d_bad);
+  KB_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
+  KB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (first_bad) *first_bad = bad;
+  if (bad != ~0ull)
+    throw ApiError(KB_ERR_INVALID_POINT, bad < ctx->srs_n ? "SRS: G1 power " + std::to_string(bad) + " is not a point of the curve"
+                                                          : std::string("SRS: [tau]_2 is not a point of the r-torsion of the twist"));
+  KB_API_END(ctx)
+}
+
+static int32_t single_msm_g1(kb_ctx* ctx, const uint32_t* scalars, uint64_t first, uint64_t n, uint32_t out_xy[16], uint8_t* out_inf) {
   KB_API_BEGIN(ctx)
   need(out_xy != nullptr && (n == 0 || scalars != nullptr), "kb_msm_g1: null pointer");
   need_srs(ctx);
@@ -213,9 +237,9 @@ int32_t kb_fr_ntt(kb_ctx* ctx, uint32_t* data, uint64_t n, int32_t inverse) {
   KB_API_END(ctx)
 }
 
-int32_t kb_encrypt_batch(kb_ctx* ctx, const uint32_t com_xy[16], uint8_t com_inf, const uint32_t* points, const uint32_t* values,
-                         const uint32_t* r, const uint8_t* msgs, const uint64_t* msg_off, uint64_t n,
-                         uint32_t* ct_g2_xy, uint8_t* ct_inf, uint8_t* msg_ct) {
+static int32_t single_encrypt_batch(kb_ctx* ctx, const uint32_t com_xy[16], uint8_t com_inf, const uint32_t* points, const uint32_t* values,
+                                    const uint32_t* r, const uint8_t* msgs, const uint64_t* msg_off, uint64_t n,
+                                    uint32_t* ct_g2_xy, uint8_t* ct_inf, uint8_t* msg_ct) {
   KB_API_BEGIN(ctx)
   need(com_xy != nullptr, "kb_encrypt_batch: null commitment");
   need(n == 0 || (points && values && r && msg_off && ct_g2_xy && ct_inf), "kb_encrypt_batch: null pointer");
@@ -235,8 +259,8 @@ int32_t kb_encrypt_batch(kb_ctx* ctx, const uint32_t com_xy[16], uint8_t com_inf
   KB_API_END(ctx)
 }
 
-int32_t kb_decrypt_batch(kb_ctx* ctx, const uint32_t* proofs_xy, const uint8_t* proofs_inf, const uint32_t* ct_g2_xy,
-                         const uint8_t* ct_inf, const uint8_t* msg_ct, const uint64_t* msg_off, uint64_t n, uint8_t* msgs_out) {
+static int32_t single_decrypt_batch(kb_ctx* ctx, const uint32_t* proofs_xy, const uint8_t* proofs_inf, const uint32_t* ct_g2_xy,
+                                    const uint8_t* ct_inf, const uint8_t* msg_ct, const uint64_t* msg_off, uint64_t n, uint8_t* msgs_out) {
   KB_API_BEGIN(ctx)
   need(n == 0 || (proofs_xy && ct_g2_xy && msg_off), "kb_decrypt_batch: null pointer");
   uint64_t total = 0;
@@ -330,6 +354,152 @@ int32_t kb_debug_fp_op(kb_ctx* ctx, int32_t field, int32_t op, const uint32_t* a
   debug_fp_op(ctx, field, op, da, db, o, n);
   o.finish();
   KB_API_END(ctx)
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-device contexts: ONE process drives all the GPUs of a box, one host thread + stream per device.
+// Every device holds the whole SRS and its fixed-base tables (HBM capacity is what a B200 has to spare), so any call
+// range splits evenly: `commit` by point range - each device returns one partial sum, the <= 8 partials (65 B each)
+// are added on the first device - and the encrypt / decrypt batches by index with no exchange at all.  All other
+// entry points run on the first device.  Peer access is enabled between the devices, so device-resident buffers of
+// any of them are legal arguments (reads and writes go over NVLink).
+// ------------------------------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+
+template <class F>
+int32_t on_all_devices(kb_ctx* ctx, F f) {   // f(k, sub-context) on one host thread per device; first failure wins
+  const size_t nd = 1 + ctx->peers.size();
+  std::vector<int32_t> rc(nd, KB_OK);
+  std::vector<std::thread> th;
+  for (size_t k = 1; k < nd; k++) th.emplace_back([&rc, &f, ctx, k] { rc[k] = f(k, ctx->peers[k - 1]); });
+  rc[0] = f(0, ctx);
+  for (auto& t : th) t.join();
+  for (int i = 0; i < KB_T_COUNT; i++)
+    for (kb_ctx* p : ctx->peers) if (p->last_ms[i] > ctx->last_ms[i]) ctx->last_ms[i] = p->last_ms[i];   // the slowest device
+  for (size_t k = 1; k < nd; k++)
+    if (rc[k] != KB_OK && rc[0] == KB_OK) { ctx->err = "device " + std::to_string(ctx->peers[k - 1]->device) + ": " + ctx->peers[k - 1]->err; return rc[k]; }
+  return rc[0];
+}
+inline uint64_t shard_lo(uint64_t n, size_t k, size_t nd) { return n / nd * k + (k < n % nd ? k : n % nd); }
+template <class T> inline const T* at(const T* p, uint64_t i) { return p ? p + i : nullptr; }
+template <class T> inline T* at(T* p, uint64_t i) { return p ? p + i : nullptr; }
+constexpr uint64_t MULTI_MIN_PER_DEVICE = 1024;   // below this a split costs more than it saves
+
+}  // namespace
+extern "C" {
+
+int32_t kb_ctx_create_multi(const int32_t* devices, int32_t ndev, kb_ctx** out) {
+  if (!out || !devices || ndev < 1 || ndev > 64) return KB_ERR_ARG;
+  *out = nullptr;
+  for (int a = 0; a < ndev; a++) for (int b = 0; b < a; b++) if (devices[a] == devices[b]) return KB_ERR_ARG;
+  std::vector<kb_ctx*> subs(ndev, nullptr);
+  std::vector<int32_t> rc(ndev, KB_OK);
+  {
+    std::vector<std::thread> th;   // the table builds of the devices run side by side
+    for (int k = 1; k < ndev; k++) th.emplace_back([&, k] { rc[k] = kb_ctx_create(devices[k], &subs[k]); });
+    rc[0] = kb_ctx_create(devices[0], &subs[0]);
+    for (auto& t : th) t.join();
+  }
+  for (int k = 0; k < ndev; k++)
+    if (rc[k] != KB_OK) { for (kb_ctx* c : subs) kb_ctx_destroy(c); return rc[k]; }
+  for (int a = 0; a < ndev; a++) {   // peer access in both directions where the hardware offers it (NVLink / NVSwitch)
+    cudaSetDevice(devices[a]);
+    for (int b = 0; b < ndev; b++) {
+      if (a == b) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) == cudaSuccess && can) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) subs[0]->peer_access = false;
+      } else subs[0]->peer_access = false;
+      cudaGetLastError();
+    }
+  }
+  subs[0]->peers.assign(subs.begin() + 1, subs.end());
+  *out = subs[0];
+  return KB_OK;
+}
+
+int32_t kb_srs_upload(kb_ctx* ctx, const uint32_t* g1_aff_xy, uint64_t n, const uint32_t* tau_g2_xy) {
+  if (!ctx) return KB_ERR_ARG;
+  if (ctx->peers.empty()) return single_srs_upload(ctx, g1_aff_xy, n, tau_g2_xy);
+  return on_all_devices(ctx, [&](size_t, kb_ctx* sub) { return single_srs_upload(sub, g1_aff_xy, n, tau_g2_xy); });
+}
+
+int32_t kb_srs_generate(kb_ctx* ctx, const uint32_t* tau, uint64_t first_power, uint64_t n, uint32_t* out_g1_xy, uint32_t* out_tau_g2_xy) {
+  if (!ctx) return KB_ERR_ARG;
+  if (ctx->peers.empty()) return single_srs_generate(ctx, tau, first_power, n, out_g1_xy, out_tau_g2_xy);
+  return on_all_devices(ctx, [&](size_t k, kb_ctx* sub) {
+    return single_srs_generate(sub, tau, first_power, n, k == 0 ? out_g1_xy : nullptr, k == 0 ? out_tau_g2_xy : nullptr);
+  });
+}
+
+int32_t kb_msm_g1(kb_ctx* ctx, const uint32_t* scalars, uint64_t first, uint64_t n, uint32_t out_xy[16], uint8_t* out_inf) {
+  if (!ctx) return KB_ERR_ARG;
+  const size_t nd = 1 + ctx->peers.size();
+  if (nd == 1 || n < MULTI_MIN_PER_DEVICE * nd || !out_xy || !scalars) return single_msm_g1(ctx, scalars, first, n, out_xy, out_inf);
+  if (!ctx->peer_access && is_device_ptr(scalars)) return fail(ctx, KB_ERR_ARG, "kb_msm_g1: device buffers need peer access between the devices of a multi-device context");
+  std::vector<uint32_t> part_xy(16 * nd);
+  std::vector<uint8_t> part_inf(nd, 1);
+  int32_t rc = on_all_devices(ctx, [&](size_t k, kb_ctx* sub) {
+    const uint64_t lo = shard_lo(n, k, nd), hi = shard_lo(n, k + 1, nd);
+    return single_msm_g1(sub, scalars + 8 * lo, first + lo, hi - lo, &part_xy[16 * k], &part_inf[k]);
+  });
+  if (rc != KB_OK) return rc;
+  const float acc_ms = ctx->last_ms[KB_T_MSM_ACC], tot_ms = ctx->last_ms[KB_T_TOTAL];
+  rc = kb_g1_sum(ctx, part_xy.data(), part_inf.data(), nd, out_xy, out_inf);
+  ctx->last_ms[KB_T_MSM_ACC] = acc_ms;
+  if (tot_ms >= 0 && ctx->last_ms[KB_T_TOTAL] >= 0) ctx->last_ms[KB_T_TOTAL] += tot_ms;   // slowest partial + the sum
+  return rc;
+}
+
+int32_t kb_encrypt_batch(kb_ctx* ctx, const uint32_t com_xy[16], uint8_t com_inf, const uint32_t* points, const uint32_t* values,
+                         const uint32_t* r, const uint8_t* msgs, const uint64_t* msg_off, uint64_t n,
+                         uint32_t* ct_g2_xy, uint8_t* ct_inf, uint8_t* msg_ct) {
+  if (!ctx) return KB_ERR_ARG;
+  const size_t nd = 1 + ctx->peers.size();
+  if (nd == 1 || n < MULTI_MIN_PER_DEVICE * nd || !msg_off || !com_xy)
+    return single_encrypt_batch(ctx, com_xy, com_inf, points, values, r, msgs, msg_off, n, ct_g2_xy, ct_inf, msg_ct);
+  if (!ctx->peer_access && (is_device_ptr(points) || is_device_ptr(ct_g2_xy)))
+    return fail(ctx, KB_ERR_ARG, "kb_encrypt_batch: device buffers need peer access between the devices of a multi-device context");
+  std::vector<uint64_t> off(n + 1);
+  uint32_t com_host[16];
+  cudaSetDevice(ctx->device);
+  if (cudaMemcpy(off.data(), msg_off, (n + 1) * 8, cudaMemcpyDefault) != cudaSuccess || cudaMemcpy(com_host, com_xy, 64, cudaMemcpyDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, KB_ERR_CUDA, "kb_encrypt_batch: cannot read msg_off / commitment");
+  }
+  return on_all_devices(ctx, [&](size_t k, kb_ctx* sub) {
+    const uint64_t lo = shard_lo(n, k, nd), hi = shard_lo(n, k + 1, nd), base = off[lo];
+    std::vector<uint64_t> loc(hi - lo + 1);
+    for (uint64_t i = lo; i <= hi; i++) loc[i - lo] = off[i] - base;
+    return single_encrypt_batch(sub, com_host, com_inf, at(points, 8 * lo), at(values, 8 * lo), at(r, 8 * lo), at(msgs, base), loc.data(), hi - lo,
+                                at(ct_g2_xy, 32 * lo), at(ct_inf, lo), at(msg_ct, base));
+  });
+}
+
+int32_t kb_decrypt_batch(kb_ctx* ctx, const uint32_t* proofs_xy, const uint8_t* proofs_inf, const uint32_t* ct_g2_xy,
+                         const uint8_t* ct_inf, const uint8_t* msg_ct, const uint64_t* msg_off, uint64_t n, uint8_t* msgs_out) {
+  if (!ctx) return KB_ERR_ARG;
+  const size_t nd = 1 + ctx->peers.size();
+  if (nd == 1 || n < MULTI_MIN_PER_DEVICE * nd || !msg_off)
+    return single_decrypt_batch(ctx, proofs_xy, proofs_inf, ct_g2_xy, ct_inf, msg_ct, msg_off, n, msgs_out);
+  if (!ctx->peer_access && (is_device_ptr(proofs_xy) || is_device_ptr(msgs_out)))
+    return fail(ctx, KB_ERR_ARG, "kb_decrypt_batch: device buffers need peer access between the devices of a multi-device context");
+  std::vector<uint64_t> off(n + 1);
+  cudaSetDevice(ctx->device);
+  if (cudaMemcpy(off.data(), msg_off, (n + 1) * 8, cudaMemcpyDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, KB_ERR_CUDA, "kb_decrypt_batch: cannot read msg_off");
+  }
+  return on_all_devices(ctx, [&](size_t k, kb_ctx* sub) {
+    const uint64_t lo = shard_lo(n, k, nd), hi = shard_lo(n, k + 1, nd), base = off[lo];
+    std::vector<uint64_t> loc(hi - lo + 1);
+    for (uint64_t i = lo; i <= hi; i++) loc[i - lo] = off[i] - base;
+    return single_decrypt_batch(sub, at(proofs_xy, 16 * lo), at(proofs_inf, lo), at(ct_g2_xy, 32 * lo), at(ct_inf, lo), at(msg_ct, base), loc.data(),
+                                hi - lo, at(msgs_out, base));
+  });
 }
 
 }  // extern "C"

@@ -35,6 +35,9 @@ struct kb_ctx {
   std::string err;
   uint64_t launches = 0;
   int sm_count = 148;
+  // multi-device context (kb_ctx_create_multi): this is the first device, `peers` are the contexts of the others
+  std::vector<kb_ctx*> peers;
+  bool peer_access = true;
 
   // SRS (affine, Montgomery), resident for the life of the context
   uint32_t* d_srs = nullptr;
@@ -208,6 +211,7 @@ void open_batch(kb_ctx* ctx, const uint32_t* d_coeffs, uint64_t d, const uint32_
 void open_all_fk(kb_ctx* ctx, const uint32_t* d_coeffs, uint64_t d, uint32_t* d_proofs, uint8_t* d_inf);
 void fk_free(kb_ctx* ctx);
 void wire_upload_consts();
+void srs_validate(kb_ctx* ctx, unsigned long long* d_first_bad);
 void g1_serialize(kb_ctx* ctx, const uint32_t* d_xy, const uint8_t* d_inf, uint64_t n, int compress, uint8_t* d_out);
 void g2_serialize(kb_ctx* ctx, const uint32_t* d_xy, const uint8_t* d_inf, uint64_t n, int compress, uint8_t* d_out);
 void g1_deserialize(kb_ctx* ctx, const uint8_t* d_in, uint64_t n, int compress, int validate, uint32_t* d_xy, uint8_t* d_inf, uint8_t* d_ok);

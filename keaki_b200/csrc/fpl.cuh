@@ -68,9 +68,9 @@ namespace lz {
 
 struct W { uint32_t v[16]; };   // 512-bit non-negative integer, little-endian limbs
 
-// q^2 as 16 limbs (an offset that is 0 mod q: keeps a0 b0 - a1 b1 non-negative)
-KB_LIMB_TABLE(q2lo, 0x275d69b1u, 0x3b5458a2u, 0x09eac101u, 0xa602072du, 0x6d96cadcu, 0x4a50189cu, 0x7a1242c8u, 0x04689e95u)
-KB_LIMB_TABLE(q2hi, 0x34c6b38du, 0x26edfa5cu, 0x16375606u, 0xb00b8551u, 0x0348d21cu, 0x599a6f7cu, 0x763cbf9cu, 0x0925c4b8u)
+// 2 q^2 as 16 limbs (an offset that is 0 mod q: keeps a0 b0 - a1 b1 non-negative for a1 < 2q, b1 < q)
+KB_LIMB_TABLE(q2lo, 0x4ebad362u, 0x76a8b144u, 0x13d58202u, 0x4c040e5au, 0xdb2d95b9u, 0x94a03138u, 0xf4248590u, 0x08d13d2au)
+KB_LIMB_TABLE(q2hi, 0x698d671au, 0x4ddbf4b8u, 0x2c6eac0cu, 0x60170aa2u, 0x0691a439u, 0xb334def8u, 0xec797f38u, 0x124b8970u)
 
 // t = a * b, plain integers.  Even/odd accumulator split as in fp.cuh: E holds the partial products whose limb
 // position i + j is even (aligned 64-bit pairs at positions 0, 2, ...), O those at odd positions (O[k] is position
@@ -112,7 +112,7 @@ KB_HD W wsub(const W& a, const W& b) {   // a - b, a >= b
   r.v[15] = subc(a.v[15], b.v[15]);
   return r;
 }
-KB_HD W wadd_q2(const W& a) {   // a + q^2
+KB_HD W wadd_q2(const W& a) {   // a + 2 q^2
   W r;
   r.v[0] = add_cc(a.v[0], q2lo(0));
 #pragma unroll
@@ -174,8 +174,9 @@ KB_HD Fp<P> redc(const W& t) {
   return r;
 }
 
-// Fq2 product, operands fully reduced:  c0 = a0 b0 - a1 b1 + q^2 (in (0, 2 q^2)),  c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1
-// (= a0 b1 + a1 b0 < 2 q^2, exact as integers because the operand sums are NOT reduced); both are below q R.
+// Fq2 product.  b fully reduced (< q per coordinate), a below 2q per coordinate (an unreduced sum of two reduced values
+// is a legal a):  c0 = a0 b0 - a1 b1 + 2 q^2 in (0, 4 q^2),  c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1 = a0 b1 + a1 b0
+// < 4 q^2 (exact as integers because the operand sums are NOT reduced); both are below q R = 5.29 q^2.
 KB_HD Fq2 fq2_mul_lazy(const Fq2& a, const Fq2& b) {
   const W t0 = mul_wide(a.c0, b.c0), t1 = mul_wide(a.c1, b.c1);
   const W t2 = mul_wide(vm::add_nr(a.c0, a.c1), vm::add_nr(b.c0, b.c1));

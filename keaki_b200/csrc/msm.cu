@@ -10,8 +10,9 @@
 //    (never stored); entries (point, window, sign) are counting-sorted by bucket with global
 //    atomics; one thread owns one bucket and accumulates its entries with XYZZ mixed additions,
 //    prefetching the next base while the current addition runs.
-//  * Bucket reduction: segments of 8 buckets by running sums, segment weight by a short
-//    double-and-add, then a tree sum.
+//  * Bucket reduction, two-digit form (msm_acc.cu launch_msm_reduce): bucket b = hi * C + lo has weight
+//    (lo + 1) + hi * C, so the weighted sum splits into column sums and row sums of the flat bucket
+//    array (independent additions), a short double-and-add over the C + R folded points and a tree sum.
 // The result leaves as canonical affine coordinates, so it is bit-identical to arkworks' for any
 // summation order.
 #include "ctx.cuh"
@@ -26,7 +27,8 @@ namespace kb {
 // window choice and table build
 // ------------------------------------------------------------------------------------------
 static int msm_choose_c(uint64_t end) {
-  if (const char* e = getenv("KB_MSM_C")) { int c = atoi(e); if (c >= 4 && c <= 24) return c; }   // tuning override
+  // tuning override; c >= 8 keeps ceil(255 / c) <= 32 windows (the digit array and the 5-bit window field of an entry)
+  if (const char* e = getenv("KB_MSM_C")) { int c = atoi(e); if (c >= 8 && c <= 24) return c; }
   if (end <= 256) return 8;
   if (end <= (1ull << 13)) return 13;   // not 12: 255 = 21 * 12 + 3 would funnel every top digit into 4 buckets
   if (end <= (1ull << 17)) return 16;

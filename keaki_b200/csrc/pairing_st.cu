@@ -18,7 +18,7 @@ namespace kb {
 
 extern __shared__ uint4 st_smem[];
 
-template <int BLOCK>
+template <int BLOCK, int NS>   // NS = slot addresses below NS are in shared memory (12, 9 or 6); 6..11 otherwise in scratch slot `address`
 struct StDevMem {
   uint4* gl;          // scratch, already offset by the global thread index
   uint32_t gstride;   // threads in the launch
@@ -32,21 +32,21 @@ struct StDevMem {
     return r;
   }
   __device__ __forceinline__ Fq2 ld(int a) const {
-    if (a < 16) {
+    if (a < NS) {
       const uint4* p = st_smem + (size_t)(4 * a) * BLOCK + threadIdx.x;
       return unpack(p[0], p[BLOCK], p[2 * BLOCK], p[3 * BLOCK]);
     }
-    const uint4* p = gl + (size_t)(4 * (a - 16)) * gstride;
+    const uint4* p = gl + (size_t)(4 * (a < 16 ? a : a - 16)) * gstride;
     return unpack(p[0], p[gstride], p[2 * (size_t)gstride], p[3 * (size_t)gstride]);
   }
   __device__ __forceinline__ void st(int a, const Fq2& x) const {
     const uint4 q0 = make_uint4(x.c0.v[0], x.c0.v[1], x.c0.v[2], x.c0.v[3]), q1 = make_uint4(x.c0.v[4], x.c0.v[5], x.c0.v[6], x.c0.v[7]);
     const uint4 q2 = make_uint4(x.c1.v[0], x.c1.v[1], x.c1.v[2], x.c1.v[3]), q3 = make_uint4(x.c1.v[4], x.c1.v[5], x.c1.v[6], x.c1.v[7]);
-    if (a < 16) {
+    if (a < NS) {
       uint4* p = st_smem + (size_t)(4 * a) * BLOCK + threadIdx.x;
       p[0] = q0; p[BLOCK] = q1; p[2 * BLOCK] = q2; p[3 * BLOCK] = q3;
     } else {
-      uint4* p = gl + (size_t)(4 * (a - 16)) * gstride;
+      uint4* p = gl + (size_t)(4 * (a < 16 ? a : a - 16)) * gstride;
       p[0] = q0; p[gstride] = q1; p[2 * (size_t)gstride] = q2; p[3 * (size_t)gstride] = q3;
     }
   }
@@ -54,14 +54,14 @@ struct StDevMem {
 
 // consts: FROB_GAMMA (18 x 16 limbs) || TW_X || TW_Y
 // mode 0: write the 96 canonical GT words; mode 1: key = BLAKE3-XOF(GT bytes), out = key XOR msg_ct.
-template <int BLOCK, int MINB>
+template <int BLOCK, int MINB, int NS>
 __global__ void __launch_bounds__(BLOCK, MINB) pairing_st_kernel(const uint32_t* __restrict__ consts, const uint32_t* __restrict__ g1,
                                                                  const uint8_t* __restrict__ g1_inf, const uint32_t* __restrict__ g2,
                                                                  const uint8_t* __restrict__ g2_inf, uint64_t n, uint4* __restrict__ scratch,
                                                                  unsigned long long* __restrict__ counter, int mode, uint32_t* __restrict__ gt_out,
                                                                  const uint8_t* __restrict__ msg_ct, const uint64_t* __restrict__ off,
                                                                  uint8_t* __restrict__ out) {
-  StDevMem<BLOCK> m;
+  StDevMem<BLOCK, NS> m;
   m.gstride = gridDim.x * BLOCK;
   m.gl = scratch + (size_t)blockIdx.x * BLOCK + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
@@ -102,15 +102,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) pairing_st_kernel(const uint32_t*
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static constexpr int ST_SMEM_PER_THREAD = 12 * 64;
-
-template <int BLOCK, int MINB>
+template <int BLOCK, int MINB, int NS>
 static void st_go(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf, uint64_t n, int mode,
                   uint32_t* d_gt, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out) {
   static bool prepared = false;
-  const int smem = BLOCK * ST_SMEM_PER_THREAD;
+  const int smem = BLOCK * NS * 64;
   if (!prepared) {
-    KB_CUDA(cudaFuncSetAttribute(pairing_st_kernel<BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KB_CUDA(cudaFuncSetAttribute(pairing_st_kernel<BLOCK, MINB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     prepared = true;
   }
   unsigned blocks = (unsigned)ctx->sm_count * MINB;
@@ -121,7 +119,7 @@ static void st_go(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, co
   DevBuf<unsigned long long> counter(ctx, 1);
   KB_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), ctx->stream));
   timer_start(ctx, KB_T_PAIRING);
-  KB_LAUNCH(ctx, (pairing_st_kernel<BLOCK, MINB>), blocks, BLOCK, smem, ctx->d_st_consts, d_g1, d_g1_inf, d_g2, d_g2_inf, n, scratch.p, counter.p,
+  KB_LAUNCH(ctx, (pairing_st_kernel<BLOCK, MINB, NS>), blocks, BLOCK, smem, ctx->d_st_consts, d_g1, d_g1_inf, d_g2, d_g2_inf, n, scratch.p, counter.p,
             mode, d_gt, d_msg_ct, d_off, d_out);
   timer_stop(ctx, KB_T_PAIRING);
 }
@@ -138,12 +136,16 @@ void st_free(kb_ctx* ctx) { cudaFree(ctx->d_st_consts); ctx->d_st_consts = nullp
 
 void st_pairing_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf, uint64_t n,
                        int mode, uint32_t* d_gt, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out) {
-  switch (ctx->st_shape) {
-    case 1: st_go<64, 4>(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out); break;
-    case 2: st_go<96, 3>(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out); break;
-    case 3: st_go<128, 1>(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out); break;
-    default: st_go<128, 2>(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out); break;
+#define KB_ST_GO(B, MB, NS) st_go<B, MB, NS>(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out)
+  switch (ctx->st_shape) {   // block, blocks per SM, on-chip slots: warps per SM / register cap
+    case 1: KB_ST_GO(128, 3, 9); break;    // 12 warps, 168 registers, F and half of S on chip
+    case 2: KB_ST_GO(128, 4, 6); break;    // 16 warps, 128 registers, F on chip
+    case 3: KB_ST_GO(64, 7, 6); break;     // 14 warps, 144 registers, F on chip
+    case 4: KB_ST_GO(96, 4, 9); break;     // 12 warps, 168 registers
+    case 5: KB_ST_GO(64, 5, 9); break;     // 10 warps, 200 registers
+    default: KB_ST_GO(128, 2, 12); break;  // 8 warps, 255 registers, F and S on chip
   }
+#undef KB_ST_GO
 }
 
 }  // namespace kb

@@ -33,11 +33,13 @@ namespace st {
 #define KB_ST_INL inline
 #endif
 
-// slot addresses: 0..5 = F (tower order c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2), 6..11 = S, 16 + k = scratch slot k
+// slot addresses: 0..5 = F (tower order c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2), 6..11 = S, 16 + k = scratch slot k.
+// The memory object decides how many of the addresses below 12 are on chip (12: F and S; 9: F and half of S; 6: F
+// only); the others fall to scratch slot `address` (6..11 are reserved for them).
 enum : int { F = 0, S = 6, G = 16,
-             G_TX = G + 0, G_TY = G + 1, G_TZ = G + 2, G_P = G + 3, G_QX = G + 4, G_QY = G + 5 };
-KB_HD constexpr int G12(int k) { return G + 8 + 6 * k; }   // k-th Fq12 of the scratch
-static constexpr int SCRATCH_SLOTS = 8 + 6 * 15;           // Fq2 slots of global scratch per thread
+             G_TX = G + 0, G_TY = G + 1, G_TZ = G + 2, G_P = G + 3, G_QX = G + 4, G_QY = G + 5, G_CONJ = G + 12 };
+KB_HD constexpr int G12(int k) { return G + 18 + 6 * k; }   // k-th saved Fq12 of the scratch
+static constexpr int SCRATCH_SLOTS = 18 + 6 * 15;           // Fq2 slots of global scratch per thread
 
 // ------------------------------------------------------------------------------------------ Fq2 level
 KB_ST_CALL Fq2 f2mul(Fq2 a, Fq2 b) { return lz::fq2_mul_lazy(a, b); }
@@ -72,19 +74,20 @@ KB_ST_INL Fq2 ld_const2(const uint32_t* p) {   // 16 limbs of a constant table
 }
 
 // ------------------------------------------------------------------------------------------ Fq6 level (slot addresses)
-// slots d..d+2 = (a..a+2) * (b..b+2) in Fq6 = Fq2[v]/(v^3 - xi); negb: use -b.  All loads precede the stores, so d may
-// alias a or b.
+// a + b without reduction (< 2q per coordinate): a valid operand of f2mul when the other operand is fully reduced
+KB_ST_INL Fq2 add_loose(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = vm::add_nr(a.c0, b.c0); r.c1 = vm::add_nr(a.c1, b.c1); return r; }
+
+// slots d..d+2 = (a..a+2) * (b..b+2) in Fq6 = Fq2[v]/(v^3 - xi) (Karatsuba: 6 products; the a-side sums stay
+// unreduced).  All loads precede the stores, so d may alias a or b.
 template <class M>
-KB_ST_CALL void f6mul(M m, int d, int a, int b, int negb) {
-#define KB_B(i) (negb ? -m.ld(b + (i)) : m.ld(b + (i)))
-  const Fq2 v0 = f2mul(m.ld(a), KB_B(0));
-  const Fq2 v1 = f2mul(m.ld(a + 1), KB_B(1));
-  const Fq2 v2 = f2mul(m.ld(a + 2), KB_B(2));
-  Fq2 c0 = f2mul(m.ld(a + 1) + m.ld(a + 2), KB_B(1) + KB_B(2)) - v1 - v2;
+KB_ST_CALL void f6mul(M m, int d, int a, int b) {
+  const Fq2 v0 = f2mul(m.ld(a), m.ld(b));
+  const Fq2 v1 = f2mul(m.ld(a + 1), m.ld(b + 1));
+  const Fq2 v2 = f2mul(m.ld(a + 2), m.ld(b + 2));
+  Fq2 c0 = f2mul(add_loose(m.ld(a + 1), m.ld(a + 2)), m.ld(b + 1) + m.ld(b + 2)) - v1 - v2;
   c0 = v0 + xi(c0);
-  const Fq2 c1 = f2mul(m.ld(a) + m.ld(a + 1), KB_B(0) + KB_B(1)) - v0 - v1 + xi(v2);
-  const Fq2 c2 = f2mul(m.ld(a) + m.ld(a + 2), KB_B(0) + KB_B(2)) - v0 - v2 + v1;
-#undef KB_B
+  const Fq2 c1 = f2mul(add_loose(m.ld(a), m.ld(a + 1)), m.ld(b) + m.ld(b + 1)) - v0 - v1 + xi(v2);
+  const Fq2 c2 = f2mul(add_loose(m.ld(a), m.ld(a + 2)), m.ld(b) + m.ld(b + 2)) - v0 - v2 + v1;
   m.st(d, c0); m.st(d + 1, c1); m.st(d + 2, c2);
 }
 // (a..a+2) * (b0 + b1 v): 5 products
@@ -92,21 +95,26 @@ template <class M>
 KB_ST_INL F6 f6m01(M& m, int a, const Fq2& b0, const Fq2& b1) {
   const Fq2 aa = f2mul(m.ld(a), b0), bb = f2mul(m.ld(a + 1), b1);
   F6 r;
-  r.c0 = xi(f2mul(m.ld(a + 1) + m.ld(a + 2), b1) - bb) + aa;
-  r.c1 = f2mul(m.ld(a) + m.ld(a + 1), b0 + b1) - aa - bb;
-  r.c2 = f2mul(m.ld(a) + m.ld(a + 2), b0) - aa + bb;
+  r.c0 = xi(f2mul(add_loose(m.ld(a + 1), m.ld(a + 2)), b1) - bb) + aa;
+  r.c1 = f2mul(add_loose(m.ld(a), m.ld(a + 1)), b0 + b1) - aa - bb;
+  r.c2 = f2mul(add_loose(m.ld(a), m.ld(a + 2)), b0) - aa + bb;
   return r;
 }
 
 // ------------------------------------------------------------------------------------------ Fq12 level (F, S on chip)
-// F <- F * B, B = the Fq12 at slots b..b+5 (conjb: its conjugate).  Karatsuba over Fq6; S is scratch.
+// F <- F * B, B = the Fq12 at slots b..b+5 (conjb: its conjugate, materialised at G_CONJ first).  Karatsuba over
+// Fq6; S is scratch.
 template <class M>
 KB_ST_CALL void f12mul(M m, int b, int conjb) {
-  f6mul(m, S, F, b, 0);                  // t0 = a0 b0
-  f6mul(m, S + 3, F + 3, b + 3, conjb);  // t1 = a1 b1
+  if (conjb) {
+    for (int i = 0; i < 3; i++) { m.st(G_CONJ + i, m.ld(b + i)); m.st(G_CONJ + 3 + i, -m.ld(b + 3 + i)); }
+    b = G_CONJ;
+  }
+  f6mul(m, S, F, b);                     // t0 = a0 b0
+  f6mul(m, S + 3, F + 3, b + 3);         // t1 = a1 b1
   for (int i = 0; i < 3; i++) m.st(F + i, m.ld(F + i) + m.ld(F + 3 + i));   // a0 + a1
-  for (int i = 0; i < 3; i++) { Fq2 y = m.ld(b + 3 + i); if (conjb) y = -y; m.st(F + 3 + i, m.ld(b + i) + y); }   // b0 + b1
-  f6mul(m, F + 3, F, F + 3, 0);          // t2
+  for (int i = 0; i < 3; i++) m.st(F + 3 + i, m.ld(b + i) + m.ld(b + 3 + i));   // b0 + b1
+  f6mul(m, F + 3, F, F + 3);             // t2
   for (int i = 0; i < 3; i++) m.st(F + 3 + i, m.ld(F + 3 + i) - m.ld(S + i) - m.ld(S + 3 + i));   // c1 = t2 - t0 - t1
   m.st(F, m.ld(S) + xi(m.ld(S + 5)));    // c0 = t0 + v t1
   m.st(F + 1, m.ld(S + 1) + m.ld(S + 3));
@@ -115,13 +123,13 @@ KB_ST_CALL void f12mul(M m, int b, int conjb) {
 // F <- F^2 (complex method: 2 Fq6 products)
 template <class M>
 KB_ST_CALL void f12sqr(M m) {
-  f6mul(m, S, F, F + 3, 0);              // t = a0 a1
+  f6mul(m, S, F, F + 3);                 // t = a0 a1
   for (int i = 0; i < 3; i++) m.st(S + 3 + i, m.ld(F + i) + m.ld(F + 3 + i));   // a0 + a1
   {                                      // a0 + v a1
     const Fq2 x0 = m.ld(F) + xi(m.ld(F + 5)), x1 = m.ld(F + 1) + m.ld(F + 3), x2 = m.ld(F + 2) + m.ld(F + 4);
     m.st(F, x0); m.st(F + 1, x1); m.st(F + 2, x2);
   }
-  f6mul(m, F, S + 3, F, 0);              // u = (a0 + a1)(a0 + v a1)
+  f6mul(m, F, S + 3, F);                 // u = (a0 + a1)(a0 + v a1)
   {                                      // c0 = u - t - v t,  c1 = 2 t
     const Fq2 t0 = m.ld(S), t1 = m.ld(S + 1), t2 = m.ld(S + 2);
     m.st(F, m.ld(F) - t0 - xi(t2));
@@ -197,16 +205,17 @@ KB_ST_INL Fq2 f2inv(const Fq2& a) {
 // F <- 1 / F: d = 1 / (a0^2 - v a1^2) in Fq6, result (a0 d, -a1 d)
 template <class M>
 KB_ST_CALL void f12inv(M m) {
-  f6mul(m, S, F, F, 0);
-  f6mul(m, S + 3, F + 3, F + 3, 0);
+  f6mul(m, S, F, F);
+  f6mul(m, S + 3, F + 3, F + 3);
   const Fq2 d0 = m.ld(S) - xi(m.ld(S + 5)), d1 = m.ld(S + 1) - m.ld(S + 3), d2 = m.ld(S + 2) - m.ld(S + 4);
   const Fq2 t0 = f2sqr(d0) - xi(f2mul(d1, d2));
   const Fq2 t1 = xi(f2sqr(d2)) - f2mul(d0, d1);
   const Fq2 t2 = f2sqr(d1) - f2mul(d0, d2);
   const Fq2 n = f2inv(f2mul(d0, t0) + xi(f2mul(d2, t1) + f2mul(d1, t2)));
   m.st(S + 3, f2mul(t0, n)); m.st(S + 4, f2mul(t1, n)); m.st(S + 5, f2mul(t2, n));
-  f6mul(m, F, F, S + 3, 0);
-  f6mul(m, F + 3, F + 3, S + 3, 1);
+  f6mul(m, F, F, S + 3);
+  f6mul(m, F + 3, F + 3, S + 3);
+  for (int i = 3; i < 6; i++) m.st(F + i, -m.ld(F + i));
 }
 
 // ------------------------------------------------------------------------------------------ Miller loop

@@ -207,6 +207,46 @@ __global__ void __launch_bounds__(128) g2_deserialize_kernel(const uint8_t* __re
   okv[i] = ok ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// SRS validation: the reference reads the ptau sections with `deserialize_uncompressed_unchecked`
+// (src/kzg/ptau.rs:266,314) and never tests the points; here every resident G1 power must be a canonical-range,
+// finite point of y^2 = x^3 + 3 (cofactor 1: on the curve = in the group) and [tau]_2 a point of the twist in the
+// r-torsion.  first_bad = smallest failing G1 index, or n when only [tau]_2 fails.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool fq_in_range(const Fq& a) {
+  uint32_t q[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) q[i] = FqParams::mod(i);
+  return u256_gt(q, a.v);
+}
+__global__ void __launch_bounds__(256) srs_validate_g1_kernel(const uint32_t* __restrict__ srs, uint64_t n, unsigned long long* __restrict__ first_bad) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const G1Affine p = ld_g1(srs + 16 * i);
+  const Fq three = Fq::one() + Fq::one() + Fq::one();
+  const bool ok = fq_in_range(p.x) && fq_in_range(p.y) && !p.is_inf() && sqr(p.y) == sqr(p.x) * p.x + three;
+  if (!ok) atomicMin(first_bad, (unsigned long long)i);
+}
+__global__ void srs_validate_tau2_kernel(const uint32_t* __restrict__ tau2, uint64_t n, unsigned long long* __restrict__ first_bad) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const G2Affine p = ld_g2(tau2);
+  bool ok = fq_in_range(p.x.c0) && fq_in_range(p.x.c1) && fq_in_range(p.y.c0) && fq_in_range(p.y.c1) && !p.is_inf();
+  if (ok) ok = sqr(p.y) == sqr(p.x) * p.x + c_wire.twist_b;
+  if (ok) {
+    uint32_t r[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) r[k] = FrParams::mod(k);
+    ok = ec_mul(to_xyzz(p), r).is_inf();
+  }
+  if (!ok) atomicMin(first_bad, (unsigned long long)n);
+}
+// *d_first_bad = ~0 if the SRS is valid
+void srs_validate(kb_ctx* ctx, unsigned long long* d_first_bad) {
+  KB_CUDA(cudaMemsetAsync(d_first_bad, 0xff, sizeof(unsigned long long), ctx->stream));
+  if (ctx->srs_n) KB_LAUNCH(ctx, srs_validate_g1_kernel, cdiv(ctx->srs_n, 256), 256, 0, ctx->d_srs, ctx->srs_n, d_first_bad);
+  KB_LAUNCH(ctx, srs_validate_tau2_kernel, 1, 32, 0, ctx->d_tau2_tab, ctx->srs_n, d_first_bad);   // entry (window 0, digit 1) = tau_2
+}
+
 void g1_serialize(kb_ctx* ctx, const uint32_t* d_xy, const uint8_t* d_inf, uint64_t n, int compress, uint8_t* d_out) {
   if (n) KB_LAUNCH(ctx, g1_serialize_kernel, cdiv(n, 128), 128, 0, d_xy, d_inf, n, compress, d_out);
 }

@@ -3,13 +3,14 @@ from __future__ import annotations
 
 import numpy as np
 
-from .kzg import KZGSetup
-from .types import G1, G2, fr_array
+from .kzg import KZGSetup, default_context
+from .types import G1, G2, fr_array, rng_or_secure
 
 
 def encrypt(rng, kzg_setup: KZGSetup, com: G1, point: int, value: int, msg: bytes):
-    """src/enc.rs:19-40 -> (key_ct: G2, msg_ct: bytes); key XOR message is fused into the kernel."""
-    r = rng.fr()
+    """src/enc.rs:19-40 -> (key_ct: G2, msg_ct: bytes); key XOR message is fused into the kernel.  rng must be
+    cryptographically secure; rng=None uses the OS CSPRNG (types.SecureFrRng)."""
+    r = rng_or_secure(rng).fr()
     n = len(msg)
     off = np.array([0, n], np.uint64)
     m = np.frombuffer(bytes(msg), np.uint8).copy() if n else np.zeros(1, np.uint8)
@@ -18,7 +19,8 @@ def encrypt(rng, kzg_setup: KZGSetup, com: G1, point: int, value: int, msg: byte
 
 
 def decrypt(proof: G1, ct, ctx=None) -> bytes:
-    """src/enc.rs:44-55"""
+    """src/enc.rs:44-55 (ctx=None: the context of the latest KZGSetup)"""
+    ctx = ctx or default_context()
     key_ct, msg_ct = ct
     n = len(msg_ct)
     off = np.array([0, n], np.uint64)

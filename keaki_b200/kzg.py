@@ -4,13 +4,26 @@ Same names, argument order and error behaviour as the reference; the arithmetic 
 is one C-ABI entry point (include/keaki_b200.h) running on the GPU."""
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 
 from . import ptau as _ptau
-from ._ffi import Context, PolynomialTooLarge
+from ._ffi import Context, InvalidSrsPoint, PolynomialTooLarge
 from .types import G1, G2, FR_MODULUS, Radix2EvaluationDomain, fr_array, fr_to_limbs, unpack_g1
 
 KZGError = PolynomialTooLarge  # the only variant (src/kzg.rs:205-209)
+
+_latest_ctx = None   # weak reference to the context of the most recently created KZGSetup
+
+
+def default_context() -> Context:
+    """Context for the reference calls that take no setup (`decapsulate`, `decrypt`, `vec_decrypt`): the one of the most
+    recently created KZGSetup (same device, no second set of tables)."""
+    ctx = _latest_ctx() if _latest_ctx is not None else None
+    if ctx is None or getattr(ctx, "h", None) is None:
+        raise RuntimeError("keaki_b200: no live KZGSetup - create one (KZGSetup.setup / new_from_file) or pass ctx= explicitly")
+    return ctx
 
 
 def _strip(p):
@@ -25,18 +38,28 @@ class KZGSetup:
     """src/kzg.rs:22-85.  Owns the GPU context; the SRS is uploaded once and stays resident."""
 
     def __init__(self, ctx: Context, g1_xy: np.ndarray, tau_g2: G2):
+        global _latest_ctx
         self.ctx = ctx
         self._g1_xy = g1_xy          # (n, 16) Montgomery affine
         self._tau_g2 = tau_g2
+        if ctx is not None:
+            _latest_ctx = weakref.ref(ctx)
 
     @classmethod
-    def new_from_file(cls, file: str, device: int = 0, ctx: Context | None = None) -> "KZGSetup":
-        """src/kzg.rs:33-52"""
+    def new_from_file(cls, file: str, device: int = 0, ctx: Context | None = None, validate: bool = True) -> "KZGSetup":
+        """src/kzg.rs:33-52.  Unlike the reference (`deserialize_uncompressed_unchecked`, src/kzg/ptau.rs:266,314) the
+        uploaded points are validated on the GPU (kb_srs_validate): a file whose elements are not points of the curve
+        is a SetupFileError("ParseError(...)") instead of a silently wrong SRS."""
         g1, g2 = _ptau.get_powers_from_file(file)
         if g2.shape[0] < 2:
             raise _ptau.SetupFileError("EmptySection(3)")
         ctx = ctx or Context(device)
         ctx.srs_upload(g1, g2[1])
+        if validate:
+            try:
+                ctx.srs_validate()
+            except InvalidSrsPoint as e:
+                raise _ptau.SetupFileError(f"ParseError({e})") from e
         return cls(ctx, g1, G2(g2[1]))
 
     @classmethod

@@ -39,16 +39,33 @@ def parse_sections(data: bytes):
         if sid not in SECTION_IDS:
             raise SetupFileError(f"UnknownSection({sid})")
         off += SECTION_HEADER_LEN
-        sections[sid] = (off, slen)
+        if off + slen > len(data):
+            raise SetupFileError("UnexpectedEof")
+        sections.setdefault(sid, (off, slen))   # a repeated id keeps its first occurrence
         off += slen
     if off != len(data):
         raise SetupFileError("SectionsNotContiguous")
     return sections
 
 
+MAX_POWER = 28   # 2-adicity of the BN254 scalar field: no larger ceremony exists (and 2^power * 128 B must stay addressable)
+
+
+def _section(sections, sid):
+    """`FileSections::get` (src/kzg/ptau.rs:146-150): a section that is not in the file is EmptySection(id)."""
+    if sid not in sections:
+        raise SetupFileError(f"EmptySection({sid})")
+    return sections[sid]
+
+
 def read_header(data: bytes, sections):
-    off, _ = sections[1]
+    """`HeaderSection::parse` (src/kzg/ptau.rs:190-222); short headers are a ParseError instead of the reference's slice panic."""
+    off, slen = _section(sections, 1)
+    if slen < 4:
+        raise SetupFileError("ParseError(header section too short)")
     n8 = struct.unpack_from("<I", data, off)[0]
+    if 4 + n8 + 8 > slen:
+        raise SetupFileError("ParseError(header section too short)")
     modulus = int.from_bytes(data[off + 4: off + 4 + n8], "little")
     power, ceremony_power = struct.unpack_from("<II", data, off + 4 + n8)
     return n8, modulus, power, ceremony_power
@@ -65,11 +82,16 @@ def get_powers_from_file(path: str):
     n8, modulus, power, _ = read_header(data, sections)
     if n8 != 32 or modulus != FQ_MODULUS:
         raise SetupFileError("InvalidFieldModulus")
+    if power > MAX_POWER:
+        raise SetupFileError(f"ParseError(power {power} > {MAX_POWER})")
     n_g1, n_g2 = 2 * (1 << power) - 1, 1 << power
-    o1, l1 = sections[2]
-    o2, l2 = sections[3]
-    if l1 < n_g1 * 64 or l2 < n_g2 * 128:
-        raise SetupFileError("SectionTooShort")
+    o1, l1 = _section(sections, 2)
+    o2, l2 = _section(sections, 3)
+    # src/kzg/ptau.rs:251-256, 299-304: the section must hold exactly the expected number of elements
+    if l1 != n_g1 * 64:
+        raise SetupFileError(f"ElementSizeMismatch({n_g1 * 64}, {l1})")
+    if l2 != n_g2 * 128:
+        raise SetupFileError(f"ElementSizeMismatch({n_g2 * 128}, {l2})")
     g1 = np.frombuffer(data, dtype=np.uint32, count=n_g1 * 16, offset=o1).reshape(n_g1, 16).copy()
     g2 = np.frombuffer(data, dtype=np.uint32, count=n_g2 * 32, offset=o2).reshape(n_g2, 32).copy()
     return g1, g2

@@ -6,6 +6,7 @@ affine Montgomery coordinates plus an infinity flag."""
 from __future__ import annotations
 
 import hashlib
+import os
 
 import numpy as np
 
@@ -137,13 +138,30 @@ def pack_g2(points):
     return xy, inf
 
 
-class FrRng:
-    """Deterministic stand-in for the reference's `rng: &mut impl rand::Rng` argument: `fr()` plays
-    `E::ScalarField::rand(rng)` (src/kem.rs:26, src/vec.rs:32) — one draw per call, in call order.
-    (arkworks' exact StdRng stream cannot be reproduced without the Rust crates; the C ABI takes the
-    drawn scalars as input, so a Rust shim keeps using arkworks' own `Fr::rand`.)"""
+class SecureFrRng:
+    """The `rng: &mut impl rand::Rng` argument of the reference backed by the operating system's CSPRNG (`os.urandom`):
+    `fr()` plays `E::ScalarField::rand(rng)` (src/kem.rs:26, src/vec.rs:32) — 254 uniformly random bits, rejected if
+    not below r.  This is what `encapsulate` / `encrypt` / `vec_encrypt` / `vec_commit` use when called with rng=None:
+    the encapsulation randomness r and the hiding pad of a vector commitment MUST be unpredictable (a repeated or
+    guessable r makes the shared secret A^r gT^(-v r) recoverable; a guessable pad makes the commitment non-hiding)."""
 
-    def __init__(self, seed: int = 0):
+    def fr(self) -> int:
+        while True:
+            v = int.from_bytes(os.urandom(32), "little") & ((1 << 254) - 1)
+            if v < FR_MODULUS:
+                return v
+
+    def bytes(self, n: int) -> bytes:
+        return os.urandom(n)
+
+
+class SeededFrRng:
+    """DETERMINISTIC stand-in for the reference's rng argument — tests, benchmarks and reproducible fixtures only; never
+    for real encryptions or commitments (see SecureFrRng).  The seed is mandatory.  `fr()` = one `Fr::rand` draw per
+    call, in call order, from a blake2b counter stream.  (arkworks' exact StdRng stream cannot be reproduced without the
+    Rust crates; the C ABI takes the drawn scalars as input, so a Rust shim keeps using arkworks' own `Fr::rand`.)"""
+
+    def __init__(self, seed: int):
         self._seed = int(seed).to_bytes(16, "little", signed=False)
         self._ctr = 0
 
@@ -163,6 +181,14 @@ class FrRng:
         while len(out) < n:
             out += self._block()
         return out[:n]
+
+
+FrRng = SeededFrRng   # historical name; the seed argument is required
+
+
+def rng_or_secure(rng):
+    """rng=None -> the OS CSPRNG (the reference takes a caller CSPRNG; a deterministic default would be a vulnerability)"""
+    return SecureFrRng() if rng is None else rng
 
 
 class Radix2EvaluationDomain:

@@ -229,7 +229,7 @@ void he_msm_digits(const uint32_t* scalar_canonical, int c, int nwin, int32_t* d
 }  // extern "C"
 
 // The compiled single-thread pairing (pairing_st.cuh) on a host slot store: GT as 384 canonical bytes.
-struct StState { Fq2 on[16]; Fq2 sc[st::SCRATCH_SLOTS]; };
+struct StState { Fq2 on[16]; Fq2 sc[st::SCRATCH_SLOTS]; };   // on-chip slots: all 12 (the split is a device-memory detail)
 struct StMem {
   StState* p;
   Fq2 ld(int a) const { return a < 16 ? p->on[a] : p->sc[a - 16]; }

@@ -39,6 +39,70 @@ def test_rng_is_deterministic_and_in_range():
     assert FrRng(6).fr() != xs[0]
 
 
+def test_default_rng_is_the_os_csprng_and_contexts_resolve_clearly():
+    """rng=None must never mean a fixed seed: SecureFrRng draws from os.urandom; the seeded generator needs an
+    explicit seed; the setup-free calls fail with a clear message when no KZGSetup exists"""
+    from keaki_b200 import kem
+    from keaki_b200.types import SecureFrRng, SeededFrRng, rng_or_secure
+    assert isinstance(rng_or_secure(None), SecureFrRng)
+    r = FrRng(1)
+    assert rng_or_secure(r) is r and isinstance(r, SeededFrRng)
+    xs = {SecureFrRng().fr() for _ in range(20)}
+    assert len(xs) == 20 and all(0 <= x < FR_MODULUS for x in xs)
+    with pytest.raises(TypeError):
+        FrRng()
+    kzg._latest_ctx = None
+    with pytest.raises(RuntimeError, match="no live KZGSetup"):
+        kem.decapsulate(G1.generator(), G2.zero(), 32)
+
+
+def test_ptau_reader_is_as_strict_as_the_reference(tmp_path):
+    """src/kzg/ptau.rs:251-256,299-304 (exact section sizes), :146-150 (missing sections), bounded power"""
+    import struct
+    g1, g2 = ptau.get_powers_from_file(os.path.join(GOLD, "ppot_0080_01_mini.ptau"))
+    good = tmp_path / "good.ptau"
+    ptau.write_ptau(str(good), g1, g2, power=1)
+    data = good.read_bytes()
+
+    def sections(blob):
+        off, out = 12, []
+        for _ in range(11):
+            sid, slen = struct.unpack_from("<IQ", blob, off)
+            out.append((sid, blob[off + 12: off + 12 + slen]))
+            off += 12 + slen
+        return out
+
+    def build(secs):
+        return data[:12] + b"".join(struct.pack("<IQ", sid, len(body)) + body for sid, body in secs)
+
+    secs = sections(data)
+    assert build(secs) == data
+    # a longer TauG1 section (one extra element) is ElementSizeMismatch, not silently accepted
+    longer = [(sid, body + bytes(64) if sid == 2 else body) for sid, body in secs]
+    p = tmp_path / "longer.ptau"; p.write_bytes(build(longer))
+    with pytest.raises(ptau.SetupFileError, match="ElementSizeMismatch"):
+        ptau.get_powers_from_file(str(p))
+    shorter = [(sid, body[:-128] if sid == 3 else body) for sid, body in secs]
+    p = tmp_path / "shorter.ptau"; p.write_bytes(build(shorter))
+    with pytest.raises(ptau.SetupFileError, match="ElementSizeMismatch"):
+        ptau.get_powers_from_file(str(p))
+    # TauG2 section replaced by a second copy of section 4: section 3 is missing -> EmptySection(3), not a KeyError
+    dup = [((4, b"") if sid == 3 else (sid, body)) for sid, body in secs]
+    p = tmp_path / "dup.ptau"; p.write_bytes(build(dup))
+    with pytest.raises(ptau.SetupFileError, match="EmptySection"):
+        ptau.get_powers_from_file(str(p))
+    # absurd power in the header
+    hdr = secs[0][1]
+    big = [(1, hdr[:36] + struct.pack("<I", 200) + hdr[40:])] + secs[1:]
+    p = tmp_path / "big.ptau"; p.write_bytes(build(big))
+    with pytest.raises(ptau.SetupFileError):
+        ptau.get_powers_from_file(str(p))
+    short_hdr = [(1, hdr[:20])] + secs[1:]
+    p = tmp_path / "hdr.ptau"; p.write_bytes(build(short_hdr))
+    with pytest.raises(ptau.SetupFileError):
+        ptau.get_powers_from_file(str(p))
+
+
 def test_points_equality_and_packing():
     g = G1.generator()
     assert g.to_affine_ints() == (1, 2) and G1.zero().inf and G1.zero() == G1(None)

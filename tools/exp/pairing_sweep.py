@@ -23,7 +23,11 @@ def rand_fr(k):
     return a
 
 
-configs = [("vm", None), ("st", "0"), ("st", "1"), ("st", "2"), ("st", "3")]
+configs = [("vm", None), ("st", "0"), ("st", "1"), ("st", "2"), ("st", "3"), ("st", "4"), ("st", "5")]
+if os.environ.get("SWEEP_ONLY"):   # e.g. SWEEP_ONLY=st:0
+    impl_, shape_ = os.environ["SWEEP_ONLY"].split(":")
+    configs = [(impl_, shape_ if shape_ != "" else None)]
+reps = int(os.environ.get("SWEEP_REPS", "4"))
 ref = None
 inputs = None
 for impl, shape in configs:
@@ -45,7 +49,7 @@ for impl, shape in configs:
         ctx.srs_generate(tau, 16, download=False)
     g1, g1i, ct, cti, mc, off = inputs
     times = []
-    for rep in range(4):
+    for rep in range(reps):
         t = time.perf_counter()
         out = ctx.decrypt_batch(g1, g1i, ct, cti, mc, off)
         times.append((time.perf_counter() - t) * 1e3)
