@@ -183,7 +183,7 @@ void g1_xyzz_sum_to_affine(kb_ctx* ctx, uint32_t* d_xyzz /* n*32, destroyed */, 
 void msm_free_tables(kb_ctx* ctx);
 void g1_mul_gen_batch(kb_ctx* ctx, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_xy, uint8_t* d_out_inf);
 void launch_msm_accumulate(kb_ctx* ctx, const uint32_t* tab, uint64_t tab_n, uint64_t first, const uint32_t* offsets,
-                           const uint32_t* entries, const uint32_t* perm, uint32_t nb, uint32_t* buckets, bool into);
+                           const uint32_t* entries, const uint32_t* perm, uint32_t nb, uint32_t* buckets, bool into, uint64_t max_entries);
 void launch_msm_reduce(kb_ctx* ctx, const uint32_t* buckets, uint32_t nb, uint32_t* d_out_xy, uint8_t* d_out_inf);
 void srs_generate(kb_ctx* ctx, const uint32_t* d_tau, uint64_t first_power, uint64_t n, uint32_t* d_tau_g2_out);
 void we_init_tables(kb_ctx* ctx);                       // G2 generator + gT tables (ctx creation)

@@ -260,7 +260,7 @@ static void msm_run(kb_ctx* ctx, const uint32_t* scalars, bool from_host, uint64
     MsmSort w(ctx, nb, n, tab.nwin);
     msm_sort(ctx, ctx->stream, w, tab, c, d_sc);
     timer_start(ctx, KB_T_MSM_ACC);
-    launch_msm_accumulate(ctx, tab.d, tab.n, first, w.offsets, w.entries, w.perm, nb, buckets, false);
+    launch_msm_accumulate(ctx, tab.d, tab.n, first, w.offsets, w.entries, w.perm, nb, buckets, false, n * tab.nwin);
     timer_stop(ctx, KB_T_MSM_ACC);
     launch_msm_reduce(ctx, buckets, nb, d_out_xy, d_out_inf);
     return;
@@ -288,9 +288,9 @@ static void msm_run(kb_ctx* ctx, const uint32_t* scalars, bool from_host, uint64
     msm_sort(ctx, side, wb, tab, c, d_sc + 8 * na);
     KB_CUDA(cudaEventRecord(ctx->ev_copy[2], side));
     timer_start(ctx, KB_T_MSM_ACC);
-    launch_msm_accumulate(ctx, tab.d, tab.n, first, wa.offsets, wa.entries, wa.perm, nb, buckets, false);
+    launch_msm_accumulate(ctx, tab.d, tab.n, first, wa.offsets, wa.entries, wa.perm, nb, buckets, false, na * tab.nwin);
     KB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[2], 0));
-    launch_msm_accumulate(ctx, tab.d, tab.n, first + na, wb.offsets, wb.entries, wb.perm, nb, buckets, true);
+    launch_msm_accumulate(ctx, tab.d, tab.n, first + na, wb.offsets, wb.entries, wb.perm, nb, buckets, true, nbp * tab.nwin);
     timer_stop(ctx, KB_T_MSM_ACC);
     launch_msm_reduce(ctx, buckets, nb, d_out_xy, d_out_inf);
   } catch (...) {

@@ -4,7 +4,11 @@
 #include "ctx.cuh"
 #include "quad.cuh"
 
+#include <algorithm>
+
 namespace kb {
+
+static constexpr uint32_t MSM_SEG = 256;   // entries one thread sums at most (see "Over-full buckets" below)
 
 // ------------------------------------------------------------------------------------------
 // bucket accumulation: one thread per bucket, XYZZ mixed additions, next base prefetched
@@ -17,6 +21,7 @@ __global__ void __launch_bounds__(256, 2) msm_accumulate_kernel(const uint32_t* 
   if (tid >= nb) return;
   const uint32_t b = perm[tid];   // buckets by decreasing population: the 32 lanes of a warp run equally long
   uint32_t lo = offsets[b], hi = offsets[b + 1];
+  if (hi - lo > MSM_SEG) hi = lo + MSM_SEG;   // the rest of an over-full bucket is summed in segments by other threads (below)
   G1 acc = into ? ld_g1x(buckets + 32 * (uint64_t)b) : G1::infinity();   // a second pass continues the first one's sums
   if (lo < hi) {
     uint32_t e = entries[lo];
@@ -35,9 +40,87 @@ __global__ void __launch_bounds__(256, 2) msm_accumulate_kernel(const uint32_t* 
   st_g1x(buckets + 32 * (uint64_t)b, acc);
 }
 
+// ------------------------------------------------------------------------------------------
+// Over-full buckets.  All windows share one bucket set, so structured scalars (all equal, 0/1 vectors, small
+// coefficients) put O(n) entries into a handful of buckets, and one thread per bucket would run O(n) dependent
+// additions.  The owner of a bucket therefore sums only its first MSM_SEG entries; the remainder is cut into segments
+// of MSM_SEG entries, each summed by a thread of its own into a partial, and the partials of a bucket are folded onto
+// it by one block.  Uniform scalars never exceed MSM_SEG (26 +- 5 entries per bucket at 2^20): the three kernels below
+// then find empty lists and return (about 10 us per call).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msm_overflow_list_kernel(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t* __restrict__ counters /* nseg, nsplit */,
+                                                                uint2* __restrict__ seg_list, uint4* __restrict__ split_list) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const uint32_t size = offsets[b + 1] - offsets[b];
+  if (size <= MSM_SEG) return;
+  const uint32_t k = (size - 1) / MSM_SEG;   // segments after the first
+  const uint32_t base = atomicAdd(&counters[0], k);
+  split_list[atomicAdd(&counters[1], 1u)] = make_uint4(b, base, k, 0u);
+  for (uint32_t j = 0; j < k; j++) seg_list[base + j] = make_uint2(b, j + 1);
+}
+__global__ void __launch_bounds__(256, 2) msm_overflow_acc_kernel(const uint32_t* __restrict__ tab, uint64_t tab_n, uint64_t first,
+                                                                  const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ entries,
+                                                                  const uint32_t* __restrict__ counters, const uint2* __restrict__ seg_list,
+                                                                  uint32_t* __restrict__ partial) {
+  const uint32_t nseg = counters[0];
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nseg; t += gridDim.x * blockDim.x) {
+    const uint2 sg = seg_list[t];
+    const uint32_t lo = offsets[sg.x] + sg.y * MSM_SEG, end = offsets[sg.x + 1];
+    const uint32_t hi = end - lo > MSM_SEG ? lo + MSM_SEG : end;
+    G1 acc = G1::infinity();
+    for (uint32_t k = lo; k < hi; k++) {
+      const uint32_t e = entries[k];
+      G1Affine cur = ld_g1(tab + 16 * ((uint64_t)((e >> 26) & 31u) * tab_n + first + (e & 0x3ffffffu)));
+      if (e >> 31) cur.y = -cur.y;
+      acc = ec_add_mixed(acc, cur);
+    }
+    st_g1x(partial + 32 * (uint64_t)t, acc);
+  }
+}
+__device__ __noinline__ G1 g1_add_cold(G1 a, G1 b) { return ec_add(a, b); }
+__global__ void __launch_bounds__(256) msm_overflow_fold_kernel(const uint32_t* __restrict__ counters, const uint4* __restrict__ split_list,
+                                                                const uint32_t* __restrict__ partial, uint32_t* __restrict__ buckets) {
+  __shared__ uint32_t sm[128 * 32];
+  const uint32_t nsplit = counters[1];
+  for (uint32_t s = blockIdx.x; s < nsplit; s += gridDim.x) {
+    const uint4 sp = split_list[s];
+    G1 acc = G1::infinity();
+    for (uint32_t i = threadIdx.x; i < sp.z; i += blockDim.x) acc = g1_add_cold(acc, ld_g1x(partial + 32 * (uint64_t)(sp.y + i)));
+    for (int half = 128; half >= 1; half >>= 1) {
+      if (threadIdx.x >= half && threadIdx.x < 2 * half) {
+        uint32_t* d = sm + 32 * (threadIdx.x - half);
+#pragma unroll
+        for (int q = 0; q < 8; q++) { d[q] = acc.x.v[q]; d[8 + q] = acc.y.v[q]; d[16 + q] = acc.zz.v[q]; d[24 + q] = acc.zzz.v[q]; }
+      }
+      __syncthreads();
+      if (threadIdx.x < half) {
+        const uint32_t* d = sm + 32 * threadIdx.x;
+        G1 o;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { o.x.v[q] = d[q]; o.y.v[q] = d[8 + q]; o.zz.v[q] = d[16 + q]; o.zzz.v[q] = d[24 + q]; }
+        acc = g1_add_cold(acc, o);
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) st_g1x(buckets + 32 * (uint64_t)sp.x, g1_add_cold(ld_g1x(buckets + 32 * (uint64_t)sp.x), acc));
+    __syncthreads();
+  }
+}
+
 void launch_msm_accumulate(kb_ctx* ctx, const uint32_t* tab, uint64_t tab_n, uint64_t first, const uint32_t* offsets,
-                           const uint32_t* entries, const uint32_t* perm, uint32_t nb, uint32_t* buckets, bool into) {
+                           const uint32_t* entries, const uint32_t* perm, uint32_t nb, uint32_t* buckets, bool into, uint64_t max_entries) {
   KB_LAUNCH(ctx, msm_accumulate_kernel, cdiv(nb, 256), 256, 0, tab, tab_n, first, offsets, entries, perm, nb, buckets, into ? 1 : 0);
+  const uint64_t max_seg = max_entries / MSM_SEG + 1;   // segments (and split buckets) there can be at most
+  DevBuf<uint32_t> counters(ctx, 2), partial(ctx, 32 * max_seg);
+  DevBuf<uint2> seg_list(ctx, max_seg);
+  DevBuf<uint4> split_list(ctx, max_seg);
+  KB_CUDA(cudaMemsetAsync(counters.p, 0, 8, ctx->stream));
+  KB_LAUNCH(ctx, msm_overflow_list_kernel, cdiv(nb, 256), 256, 0, offsets, nb, counters.p, seg_list.p, split_list.p);
+  const unsigned acc_blocks = (unsigned)std::min<uint64_t>(cdiv(max_seg, 256), 2ull * ctx->sm_count);
+  KB_LAUNCH(ctx, msm_overflow_acc_kernel, acc_blocks, 256, 0, tab, tab_n, first, offsets, entries, counters.p, seg_list.p, partial.p);
+  const unsigned fold_blocks = (unsigned)std::min<uint64_t>(max_seg, 4ull * ctx->sm_count);
+  KB_LAUNCH(ctx, msm_overflow_fold_kernel, fold_blocks, 256, 0, counters.p, split_list.p, partial.p, buckets);
 }
 
 

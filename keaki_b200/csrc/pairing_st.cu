@@ -137,12 +137,15 @@ void st_free(kb_ctx* ctx) { cudaFree(ctx->d_st_consts); ctx->d_st_consts = nullp
 void st_pairing_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf, uint64_t n,
                        int mode, uint32_t* d_gt, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out) {
 #define KB_ST_GO(B, MB, NS) st_go<B, MB, NS>(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out)
-  switch (ctx->st_shape) {   // block, blocks per SM, on-chip slots: warps per SM / register cap
-    case 1: KB_ST_GO(128, 3, 9); break;    // 12 warps, 168 registers, F and half of S on chip
-    case 2: KB_ST_GO(128, 4, 6); break;    // 16 warps, 128 registers, F on chip
-    case 3: KB_ST_GO(64, 7, 6); break;     // 14 warps, 144 registers, F on chip
-    case 4: KB_ST_GO(96, 4, 9); break;     // 12 warps, 168 registers
-    case 5: KB_ST_GO(64, 5, 9); break;     // 10 warps, 200 registers
+  // Launch shape: 8 warps per SM at 255 registers (two blocks of 128) is the measured optimum on B200 (2^16 pairings:
+  // 25.5 ms; 7 warps in one block 27.1, 6 warps 29.5, 12 warps at 168 registers 38.0, 16 warps at 128 registers 37.1 -
+  // fewer registers cost more in spills and lost instruction-level parallelism than the extra warps bring).
+  const int shape = ctx->st_shape;
+  switch (shape) {   // block, blocks per SM, on-chip slots
+    case 5: KB_ST_GO(160, 1, 12); break;   // 5 warps, 255 registers
+    case 6: KB_ST_GO(192, 1, 12); break;   // 6 warps
+    case 7: KB_ST_GO(224, 1, 12); break;   // 7 warps
+    case 12: KB_ST_GO(128, 3, 9); break;   // 12 warps, 168 registers, half of S in the scratch (measured slower: spills)
     default: KB_ST_GO(128, 2, 12); break;  // 8 warps, 255 registers, F and S on chip
   }
 #undef KB_ST_GO

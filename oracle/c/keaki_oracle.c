@@ -596,6 +596,37 @@ void ko_msm_g1(const uint64_t* bases_xy, const uint64_t* scalars_mont, size_t n,
   g1a r; g1j_to_affine(&r, &total); store_g1(out_xy, out_inf, 0, &r);
 }
 
+/* Harness helper (NOT part of the reference path): out[i] = (i + 1) * base for i < n - n distinct valid bases for the
+ * timed CPU arm, so that bench.py --impl reference runs the MSM on as many DISTINCT points as the GPU arm does.  Chunks of
+ * repeated mixed additions, one shared inversion per chunk for the affine normalisation. */
+void ko_g1_multiples(const uint64_t* base_xy, size_t n, uint64_t* out_xy, int threads) {
+  ko_init();
+  g1a b; load_g1(&b, base_xy, NULL, 0);
+  const size_t CH = 4096;
+  long nch = (long)((n + CH - 1) / CH);
+#pragma omp parallel for schedule(dynamic) num_threads(threads)
+  for (long c = 0; c < nch; c++) {
+    size_t lo = (size_t)c * CH, hi = lo + CH < n ? lo + CH : n, m = hi - lo;
+    g1j* pts = (g1j*)malloc(m * sizeof(g1j));
+    fe* pref = (fe*)malloc(m * sizeof(fe));
+    g1j bj = {b.x, b.y, FQ.one}, cur;
+    uint64_t k[4] = {(uint64_t)lo + 1, 0, 0, 0};
+    g1j_mul(&cur, &bj, k);
+    for (size_t i = 0; i < m; i++) { pts[i] = cur; g1j_add_mixed(&cur, &cur, &b); }
+    fe acc = FQ.one, inv;
+    for (size_t i = 0; i < m; i++) { pref[i] = acc; qmul(&acc, &acc, &pts[i].z); }
+    f_inv(&FQ, &inv, &acc);
+    for (size_t i = m; i-- > 0;) {
+      fe zi, zi2, zi3; g1a a;
+      qmul(&zi, &inv, &pref[i]); qmul(&inv, &inv, &pts[i].z);
+      qsqr(&zi2, &zi); qmul(&zi3, &zi2, &zi);
+      qmul(&a.x, &pts[i].x, &zi2); qmul(&a.y, &pts[i].y, &zi3); a.inf = 0;
+      store_g1(out_xy, NULL, lo + i, &a);
+    }
+    free(pts); free(pref);
+  }
+}
+
 void ko_g1_mul(const uint64_t* p_xy, uint8_t p_inf, const uint64_t* k_mont, uint64_t* out_xy, uint8_t* out_inf) {
   ko_init();
   g1a p; load_g1(&p, p_xy, &p_inf, 0);

@@ -52,6 +52,13 @@ def msm_g1(bases_xy, scalars, threads=1):
     return out, int(inf[0])
 
 
+def g1_multiples(base_xy, n, threads=1):
+    """harness helper: (n, 16) u32 array of (i + 1) * base, i < n - distinct valid bases for the timed CPU arm"""
+    out = np.zeros((n, 16), np.uint32)
+    load().ko_g1_multiples(_p(np.ascontiguousarray(base_xy, np.uint32)), ctypes.c_size_t(n), _p(out), int(threads))
+    return out
+
+
 def g1_mul(p_xy, p_inf, k_limbs):
     out, inf = np.zeros(16, np.uint32), np.zeros(1, np.uint8)
     load().ko_g1_mul(_p(np.ascontiguousarray(p_xy, np.uint32)), ctypes.c_uint8(int(p_inf)), _p(np.ascontiguousarray(k_limbs, np.uint32)), _p(out), _p(inf))

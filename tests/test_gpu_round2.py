@@ -274,3 +274,35 @@ def test_srs_validate(ctx, tmp_path):
     with pytest.raises(ptau.SetupFileError):
         kzg.KZGSetup.new_from_file(str(path), ctx=ctx)
     assert len(kzg.KZGSetup.new_from_file(str(path), ctx=ctx, validate=False)) == 3
+
+
+def test_msm_structured_scalars_do_not_serialise(ctx):
+    """all windows share one bucket set, so all-equal / 0-1 / small scalars put O(n) entries into a few
+    buckets.  Over-full buckets are summed in segments by many threads: the result is exact and a 2^20 commit of such a
+    polynomial stays within a small multiple of the uniform case instead of one thread running 2^20 additions."""
+    n = 1 << 20
+    ctx.srs_generate(L.fr_m(TAU), n, download=False)
+    geo = (pow(TAU, n, bn.R) - 1) * pow(TAU - 1, -1, bn.R) % bn.R          # sum_i tau^i
+    uniform = rand_fr_limbs(n)
+    ctx.msm_g1(uniform)
+    ctx.msm_g1(uniform)
+    t_uniform = ctx.last_kernel_ms(0)
+    for k in (1, 7, bn.R - 1, 0x0FEDCBA987654321FEDCBA987654321FEDCBA987654321FEDCBA98765432 % bn.R):
+        sc = np.ascontiguousarray(np.tile(L.fr_m(k), (n, 1)))
+        xy, inf = ctx.msm_g1(sc)
+        ms = ctx.last_kernel_ms(0)
+        assert g1_out(xy, inf) == bn.g1_mul(bn.G1_GEN, k * geo % bn.R)
+        assert ms < 12 * t_uniform + 5.0, f"all-equal scalars {k:#x}: {ms:.1f} ms vs {t_uniform:.1f} ms uniform"
+    # 0/1 vector (a bit-vector polynomial, what a laconic-OT receiver commits to before the inverse transform)
+    bits = nprng.integers(0, 2, size=n)
+    sc = np.ascontiguousarray(np.where(bits[:, None] == 1, L.fr_m(1)[None, :], L.fr_m(0)[None, :]).astype(np.uint32))
+    xy, inf = ctx.msm_g1(sc)
+    ms = ctx.last_kernel_ms(0)
+    acc, t = 0, 1
+    tau_pows = None
+    # sum over set bits of tau^i: Horner over the bit list
+    acc = 0
+    for b in reversed(bits.tolist()):
+        acc = (acc * TAU + b) % bn.R
+    assert g1_out(xy, inf) == bn.g1_mul(bn.G1_GEN, acc)
+    assert ms < 12 * t_uniform + 5.0, f"0/1 scalars: {ms:.1f} ms vs {t_uniform:.1f} ms uniform"

@@ -23,7 +23,7 @@ def rand_fr(k):
     return a
 
 
-configs = [("vm", None), ("st", "0"), ("st", "1"), ("st", "2"), ("st", "3"), ("st", "4"), ("st", "5")]
+configs = [("vm", None), ("st", "0"), ("st", "8"), ("st", "7"), ("st", "6"), ("st", "5")]
 if os.environ.get("SWEEP_ONLY"):   # e.g. SWEEP_ONLY=st:0
     impl_, shape_ = os.environ["SWEEP_ONLY"].split(":")
     configs = [(impl_, shape_ if shape_ != "" else None)]
