@@ -174,11 +174,23 @@ class ClockSampler:
         return self.summary()
 
 
+_R_LIMBS = np.array([0xf0000001, 0x43e1f593, 0x79b97091, 0x2833e848, 0x8181585d, 0xb85045b6, 0xe131a029, 0x30644e72], dtype=np.uint64)
+
+
 def rand_fr_limbs(rng, n):
-    """n uniformly random field elements as Montgomery limbs (any value < r is a valid Montgomery image)."""
-    a = rng.integers(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
-    a[:, 7] &= 0x0FFFFFFF  # < 2^252 < r
-    return a
+    """n field elements UNIFORM below r as Montgomery limbs (any value < r is the Montgomery image of exactly one scalar, so
+    uniform limbs below r are uniform scalars): 254 random bits, rejected when not below r - what `Fr::rand` does."""
+    out = np.empty((0, 8), np.uint32)
+    while out.shape[0] < n:
+        m = int((n - out.shape[0]) * 1.4) + 16
+        a = rng.integers(0, 1 << 32, size=(m, 8), dtype=np.uint64)
+        a[:, 7] &= 0x3FFFFFFF
+        lt = np.zeros(m, bool); eq = np.ones(m, bool)
+        for k in range(7, -1, -1):      # lexicographic compare from the top limb
+            lt |= eq & (a[:, k] < _R_LIMBS[k])
+            eq &= a[:, k] == _R_LIMBS[k]
+        out = np.concatenate([out, a[lt].astype(np.uint32)])
+    return np.ascontiguousarray(out[:n])
 
 
 def dist_setup(gpus):

@@ -63,23 +63,28 @@ int32_t kb_ctx_create(int32_t device, kb_ctx** out) {
       KB_CUDA(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio));
     }
     for (auto& e : ctx->ev_copy) KB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    cudaMemPool_t pool;
-    KB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thresh = UINT64_MAX;
-    KB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-    // the generic (call-based) pairing keeps Fq12 temporaries on the per-thread stack
-    KB_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024));
+    {   // a pool of the context's own (kept warm between calls; the device's default pool and a co-resident framework's are not touched)
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = device;
+      KB_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
+      uint64_t thresh = UINT64_MAX;
+      KB_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    }
     for (auto& e : ctx->ev) KB_CUDA(cudaEventCreate(&e));
     we_upload_consts();
     wire_upload_consts();
+    st_init(ctx);   // before the WE tables: gT = e(G1, G2) is computed by the compiled pairing kernel
     we_init_tables(ctx);
     vm_init(ctx);
-    st_init(ctx);
     if (const char* e = getenv("KB_PAIRING_IMPL")) ctx->pairing_impl = (e[0] == 'v') ? 0 : 1;   // tuning override
     KB_CUDA(cudaStreamSynchronize(ctx->stream));
   } catch (const std::exception& e) {
     fprintf(stderr, "kb_ctx_create: %s\n", e.what());
-    delete ctx;
+    cudaGetLastError();
+    kb_ctx_destroy(ctx);   // frees whatever was created so far (every member starts null)
     cudaGetLastError();
     return KB_ERR_CUDA;
   }
@@ -92,7 +97,7 @@ void kb_ctx_destroy(kb_ctx* ctx) {
   for (kb_ctx* p : ctx->peers) kb_ctx_destroy(p);
   ctx->peers.clear();
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   msm_free_tables(ctx);
   fk_free(ctx);
   we_free(ctx);
@@ -103,6 +108,7 @@ void kb_ctx_destroy(kb_ctx* ctx) {
   for (auto& e : ctx->ev_copy) if (e) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   delete ctx;
 }
 

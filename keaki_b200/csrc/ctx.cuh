@@ -30,6 +30,7 @@ enum { KB_T_TOTAL = 0, KB_T_MSM_ACC = 1, KB_T_PAIRING = 2, KB_T_ENCRYPT = 3, KB_
 struct kb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;         // private stream-ordered pool for the scratch of every call (the device's default pool is left alone)
   cudaStream_t copy_stream = nullptr;   // host-to-device copies that overlap the main stream's kernels (msm_g1_host)
   cudaEvent_t ev_copy[4] = {};
   std::string err;
@@ -72,7 +73,7 @@ struct kb_ctx {
 
   // FK open-all cache: hat_s = DFT_2d(reversed SRS prefix) per d
   struct FkCache { uint64_t d = 0; uint32_t* d_hat_s = nullptr; };
-  std::vector<FkCache> fk_cache;
+  std::vector<FkCache> fk_cache;        // at most KB_FK_CACHE_MAX entries, oldest evicted (256 MiB per entry at d = 2^20)
 
   cudaEvent_t ev[2 * kb::KB_T_COUNT] = {};
   float last_ms[kb::KB_T_COUNT] = {-1.f, -1.f, -1.f, -1.f};
@@ -86,7 +87,7 @@ struct DevBuf {
   T* p = nullptr;
   cudaStream_t s;
   DevBuf(kb_ctx* ctx, size_t count) : s(ctx->stream) {
-    if (count) KB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), s));
+    if (count) KB_CUDA(cudaMallocFromPoolAsync((void**)&p, count * sizeof(T), ctx->pool, s));
   }
   ~DevBuf() { if (p) cudaFreeAsync(p, s); }
   DevBuf(const DevBuf&) = delete;
@@ -111,7 +112,7 @@ struct DevIn {
   DevIn(kb_ctx* ctx, const T* src, size_t count) : s(ctx->stream) {
     if (!src || !count) return;
     if (is_device_ptr(src)) { p = src; return; }
-    KB_CUDA(cudaMallocAsync((void**)&owned, count * sizeof(T), s));
+    KB_CUDA(cudaMallocFromPoolAsync((void**)&owned, count * sizeof(T), ctx->pool, s));
     KB_CUDA(cudaMemcpyAsync(owned, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
     p = owned;
   }
@@ -132,7 +133,7 @@ struct DevOut {
   DevOut(kb_ctx* ctx, T* dst, size_t count_) : count(count_), s(ctx->stream) {
     if (!dst || !count) return;
     if (is_device_ptr(dst)) { p = dst; return; }
-    KB_CUDA(cudaMallocAsync((void**)&owned, count * sizeof(T), s));
+    KB_CUDA(cudaMallocFromPoolAsync((void**)&owned, count * sizeof(T), ctx->pool, s));
     p = owned; host = dst;
   }
   void finish() { if (owned && host) KB_CUDA(cudaMemcpyAsync(host, owned, count * sizeof(T), cudaMemcpyDeviceToHost, s)); }

@@ -29,13 +29,14 @@ namespace kb {
 static int msm_choose_c(uint64_t end) {
   // tuning override; c >= 8 keeps ceil(255 / c) <= 32 windows (the digit array and the 5-bit window field of an entry)
   if (const char* e = getenv("KB_MSM_C")) { int c = atoi(e); if (c >= 8 && c <= 24) return c; }
-  if (end <= 256) return 8;
-  if (end <= (1ull << 13)) return 13;   // not 12: 255 = 21 * 12 + 3 would funnel every top digit into 4 buckets
-  if (end <= (1ull << 17)) return 16;
+  // measured on B200 (tools/exp/msm_c_sweep.py): c = 17 wins from 2^12 to 2^16 points, c = 20 from 2^17 on;
+  // both divide 255 into windows whose TOP window is full (255 = 15 x 17 = 12 x 20 + 15) - a short top window (c = 13: 7 bits,
+  // c = 14 or 18: 3 bits) funnels every top digit into a few dozen buckets, whose owners then run n / 48 dependent additions
+  if (end <= (1ull << 16)) return 17;
   return 20;
 }
 static uint64_t msm_table_cap(int c, uint64_t srs_n) {
-  uint64_t cap = c == 8 ? 256 : c == 13 ? (1ull << 13) : c == 16 ? (1ull << 17) : srs_n;
+  uint64_t cap = c == 17 ? (1ull << 16) : srs_n;
   if (getenv("KB_MSM_C")) cap = srs_n;
   return cap < srs_n ? cap : srs_n;
 }

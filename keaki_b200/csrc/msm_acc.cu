@@ -8,7 +8,10 @@
 
 namespace kb {
 
-static constexpr uint32_t MSM_SEG = 256;   // entries one thread sums at most (see "Over-full buckets" below)
+// entries one thread sums at most (see "Over-full buckets" below): above the largest bucket uniform scalars produce
+// (26 +- 5 at 2^20 - 109 in the 12,388 buckets the 15-bit top window of a scalar below r reaches - 32 +- 6 at 2^16) and short enough that a lone thread's chain (5 us per dependent addition) stays
+// well below the kernel's own time
+static constexpr uint32_t MSM_SEG = 128;
 
 // ------------------------------------------------------------------------------------------
 // bucket accumulation: one thread per bucket, XYZZ mixed additions, next base prefetched
@@ -43,10 +46,10 @@ __global__ void __launch_bounds__(256, 2) msm_accumulate_kernel(const uint32_t* 
 // ------------------------------------------------------------------------------------------
 // Over-full buckets.  All windows share one bucket set, so structured scalars (all equal, 0/1 vectors, small
 // coefficients) put O(n) entries into a handful of buckets, and one thread per bucket would run O(n) dependent
-// additions.  The owner of a bucket therefore sums only its first MSM_SEG entries; the remainder is cut into segments
+// additions (5 us each for a lone thread).  The owner of a bucket therefore sums only its first MSM_SEG entries; the remainder is cut into segments
 // of MSM_SEG entries, each summed by a thread of its own into a partial, and the partials of a bucket are folded onto
-// it by one block.  Uniform scalars never exceed MSM_SEG (26 +- 5 entries per bucket at 2^20): the three kernels below
-// then find empty lists and return (about 10 us per call).
+// it (a thread for a few segments, a block for many).  Uniform scalars stay below MSM_SEG: the kernels below then find
+// empty lists and return (about 20 us per call).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) msm_overflow_list_kernel(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t* __restrict__ counters /* nseg, nsplit */,
                                                                 uint2* __restrict__ seg_list, uint4* __restrict__ split_list) {
@@ -79,12 +82,27 @@ __global__ void __launch_bounds__(256, 2) msm_overflow_acc_kernel(const uint32_t
   }
 }
 __device__ __noinline__ G1 g1_add_cold(G1 a, G1 b) { return ec_add(a, b); }
+// buckets with few segments (the common case: a bucket slightly over the threshold): one thread adds them in sequence
+static constexpr uint32_t MSM_FOLD_SERIAL = 8;
+__global__ void __launch_bounds__(128) msm_overflow_fold_small_kernel(const uint32_t* __restrict__ counters, const uint4* __restrict__ split_list,
+                                                                      const uint32_t* __restrict__ partial, uint32_t* __restrict__ buckets) {
+  const uint32_t nsplit = counters[1];
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nsplit; s += gridDim.x * blockDim.x) {
+    const uint4 sp = split_list[s];
+    if (sp.z > MSM_FOLD_SERIAL) continue;
+    G1 acc = ld_g1x(buckets + 32 * (uint64_t)sp.x);
+    for (uint32_t i = 0; i < sp.z; i++) acc = g1_add_cold(acc, ld_g1x(partial + 32 * (uint64_t)(sp.y + i)));
+    st_g1x(buckets + 32 * (uint64_t)sp.x, acc);
+  }
+}
+// buckets with many segments: one block per bucket, strided partial sums + a shared-memory tree
 __global__ void __launch_bounds__(256) msm_overflow_fold_kernel(const uint32_t* __restrict__ counters, const uint4* __restrict__ split_list,
                                                                 const uint32_t* __restrict__ partial, uint32_t* __restrict__ buckets) {
   __shared__ uint32_t sm[128 * 32];
   const uint32_t nsplit = counters[1];
   for (uint32_t s = blockIdx.x; s < nsplit; s += gridDim.x) {
     const uint4 sp = split_list[s];
+    if (sp.z <= MSM_FOLD_SERIAL) continue;   // block-uniform
     G1 acc = G1::infinity();
     for (uint32_t i = threadIdx.x; i < sp.z; i += blockDim.x) acc = g1_add_cold(acc, ld_g1x(partial + 32 * (uint64_t)(sp.y + i)));
     for (int half = 128; half >= 1; half >>= 1) {
@@ -119,7 +137,9 @@ void launch_msm_accumulate(kb_ctx* ctx, const uint32_t* tab, uint64_t tab_n, uin
   KB_LAUNCH(ctx, msm_overflow_list_kernel, cdiv(nb, 256), 256, 0, offsets, nb, counters.p, seg_list.p, split_list.p);
   const unsigned acc_blocks = (unsigned)std::min<uint64_t>(cdiv(max_seg, 256), 2ull * ctx->sm_count);
   KB_LAUNCH(ctx, msm_overflow_acc_kernel, acc_blocks, 256, 0, tab, tab_n, first, offsets, entries, counters.p, seg_list.p, partial.p);
-  const unsigned fold_blocks = (unsigned)std::min<uint64_t>(max_seg, 4ull * ctx->sm_count);
+  const unsigned small_blocks = (unsigned)std::min<uint64_t>(cdiv(max_seg, 128), 4ull * ctx->sm_count);
+  KB_LAUNCH(ctx, msm_overflow_fold_small_kernel, small_blocks, 128, 0, counters.p, split_list.p, partial.p, buckets);
+  const unsigned fold_blocks = (unsigned)std::min<uint64_t>(max_seg, 2ull * ctx->sm_count);
   KB_LAUNCH(ctx, msm_overflow_fold_kernel, fold_blocks, 256, 0, counters.p, split_list.p, partial.p, buckets);
 }
 

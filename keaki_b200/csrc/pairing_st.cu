@@ -5,8 +5,8 @@
 // One thread per pairing.  F and S (12 Fq2 slots) in shared memory as [slot][quarter][thread] uint4, so every
 // access of a warp is 512 contiguous bytes; the G2 accumulator, P, Q and the saved Fq12 values of the final
 // exponentiation in a per-thread global scratch with the same layout.  The kernel is persistent: a warp takes 32
-// pairings at a time from its block's queue, so the scratch is sized by the resident threads and the tail of the
-// batch spreads evenly over all SMs.  GT never leaves the chip on the decrypt path: canonical bytes -> BLAKE3 XOF -> XOR
+// pairings at a time from a global counter, so the scratch is sized by the resident threads and the tail of the
+// batch spreads over all SMs (dealing the tasks to the blocks statically was measured: 28.7 ms against 25.5 at 2^16).  GT never leaves the chip on the decrypt path: canonical bytes -> BLAKE3 XOF -> XOR
 // happen in the epilogue.
 #include "ctx.cuh"
 #include "blake3.cuh"
@@ -53,33 +53,24 @@ struct StDevMem {
 };
 
 // consts: FROB_GAMMA (18 x 16 limbs) || TW_X || TW_Y
-// mode 0: write the 96 canonical GT words; mode 1: key = BLAKE3-XOF(GT bytes), out = key XOR msg_ct.
+// mode 0: write the 96 canonical GT words; mode 1: key = BLAKE3-XOF(GT bytes), out = key XOR msg_ct; mode 2: the 96
+// Montgomery limbs of GT.
 template <int BLOCK, int MINB, int NS>
 __global__ void __launch_bounds__(BLOCK, MINB) pairing_st_kernel(const uint32_t* __restrict__ consts, const uint32_t* __restrict__ g1,
                                                                  const uint8_t* __restrict__ g1_inf, const uint32_t* __restrict__ g2,
                                                                  const uint8_t* __restrict__ g2_inf, uint64_t n, uint4* __restrict__ scratch,
-                                                                 int mode, uint32_t* __restrict__ gt_out,
+                                                                 unsigned long long* __restrict__ counter, int mode, uint32_t* __restrict__ gt_out,
                                                                  const uint8_t* __restrict__ msg_ct, const uint64_t* __restrict__ off,
                                                                  uint8_t* __restrict__ out) {
   StDevMem<BLOCK, NS> m;
   m.gstride = gridDim.x * BLOCK;
   m.gl = scratch + (size_t)blockIdx.x * BLOCK + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
-  // Work distribution: warp tasks of 32 pairings.  Task t belongs to block t mod gridDim (static), the warps of a block
-  // take their block's tasks in order (dynamic, one shared-memory counter).  Every SM therefore runs the same number of
-  // tasks (+-1 per block) in the last, partly filled round - a single global queue lets the SMs whose warps finish
-  // first take whole extra rounds while others idle (2^16 pairings: 25.5 -> 23.9 ms).
-  __shared__ unsigned int next_task;
-  if (threadIdx.x == 0) next_task = 0;
-  __syncthreads();
-  const uint64_t tasks = (n + 31) / 32;
   for (;;) {
-    unsigned int k = 0;
-    if (lane == 0) k = atomicAdd(&next_task, 1u);
-    k = __shfl_sync(0xffffffffu, k, 0);
-    const uint64_t task = (uint64_t)k * gridDim.x + blockIdx.x;
-    if (task >= tasks) break;
-    const uint64_t base = task * 32;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
     const uint64_t i = base + lane;
     const bool live = i < n;
     const uint64_t j = live ? i : n - 1;   // padding lanes recompute the last pairing
@@ -91,6 +82,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) pairing_st_kernel(const uint32_t*
     m.st(st::G_P, P); m.st(st::G_QX, qx); m.st(st::G_QY, qy);
     st::miller(m, consts + 18 * 16);
     st::final_exp(m, consts);
+    if (mode == 2) {   // the GT element itself, Montgomery limbs in tower order (per-commitment setup of the encryption tables)
+      if (live) {
+#pragma unroll 1
+        for (int s = 0; s < 6; s++) {
+          Fq2 x = m.ld(st::F + s);
+          if (trivial) x = s == 0 ? Fq2::one() : Fq2::zero();
+          fp_store<FqParams>(gt_out + 96 * i + 16 * s, x.c0);
+          fp_store<FqParams>(gt_out + 96 * i + 16 * s + 8, x.c1);
+        }
+      }
+      continue;
+    }
     uint32_t w[96];
     st::gt_words(m, w);
     if (trivial) {   // arkworks skips pairs with an infinity: GT = 1
@@ -126,8 +129,10 @@ static void st_go(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, co
   if (blocks > need) blocks = need;
   const size_t threads = (size_t)blocks * BLOCK;
   DevBuf<uint4> scratch(ctx, (size_t)st::SCRATCH_SLOTS * 4 * threads);
+  DevBuf<unsigned long long> counter(ctx, 1);
+  KB_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), ctx->stream));
   timer_start(ctx, KB_T_PAIRING);
-  KB_LAUNCH(ctx, (pairing_st_kernel<BLOCK, MINB, NS>), blocks, BLOCK, smem, ctx->d_st_consts, d_g1, d_g1_inf, d_g2, d_g2_inf, n, scratch.p,
+  KB_LAUNCH(ctx, (pairing_st_kernel<BLOCK, MINB, NS>), blocks, BLOCK, smem, ctx->d_st_consts, d_g1, d_g1_inf, d_g2, d_g2_inf, n, scratch.p, counter.p,
             mode, d_gt, d_msg_ct, d_off, d_out);
   timer_stop(ctx, KB_T_PAIRING);
 }

@@ -275,6 +275,11 @@ void open_all_fk(kb_ctx* ctx, const uint32_t* d_coeffs, uint64_t d, uint32_t* d_
     KB_LAUNCH(ctx, fk_build_s_kernel, cdiv(n2, 256), 256, 0, ctx->d_srs, (uint32_t)d, hat_s);
     g1_ntt_dev(ctx, hat_s, logd + 1, false);
     kb_ctx::FkCache c; c.d = d; c.d_hat_s = hat_s;
+    if (ctx->fk_cache.size() >= 4) {   // bounded: the oldest transform goes (the stream is idle between calls: entries are never in use here)
+      KB_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->fk_cache.front().d_hat_s);
+      ctx->fk_cache.erase(ctx->fk_cache.begin());
+    }
     ctx->fk_cache.push_back(c);
   }
   DevBuf<uint32_t> a(ctx, 8 * (size_t)n2), h(ctx, 32 * (size_t)n2);

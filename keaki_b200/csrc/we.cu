@@ -127,15 +127,6 @@ __global__ void __launch_bounds__(128) gt_table_fill_kernel(const uint32_t* __re
   st_fq12(tab + 96 * (size_t)t, acc);
 }
 
-// single pairing e(P, G2gen) -> Montgomery Fq12 (for A = e(com, G2) and gT = e(G1, G2))
-__global__ void pairing_with_g2gen_kernel(const uint32_t* __restrict__ p_xy, uint32_t p_inf, const uint32_t* __restrict__ g2_gen,
-                                          uint32_t* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  G1Affine p = p_inf ? G1Affine::infinity() : ld_g1(p_xy);
-  G2Affine q = ld_g2(g2_gen);
-  st_fq12(out, final_exponentiation(miller_loop(p, q, c_pc), c_pc));
-}
-
 static void build_g2_table(kb_ctx* ctx, const uint32_t* d_base_xy, uint32_t* d_tab) {
   DevBuf<uint32_t> bases(ctx, WE_WIN * 64);
   KB_LAUNCH(ctx, g2_window_bases_kernel, 1, 32, 0, d_base_xy, bases);
@@ -144,10 +135,19 @@ static void build_g2_table(kb_ctx* ctx, const uint32_t* d_base_xy, uint32_t* d_t
 static void build_g2_table16(kb_ctx* ctx, const uint32_t* d_tab8, uint32_t* d_tab16) {
   KB_LAUNCH(ctx, g2_table16_kernel, cdiv((uint64_t)WE_WIN16 * WE_ENT16, 128), 128, 0, d_tab8, d_tab16);
 }
-static void build_gt_table(kb_ctx* ctx, const uint32_t* d_a, uint32_t* d_tab) {
-  DevBuf<uint32_t> bases(ctx, WE_WIN * 96);
+static void build_gt_table(kb_ctx* ctx, const uint32_t* d_a, uint32_t* d_tab, uint32_t* d_bases_out = nullptr) {
+  DevBuf<uint32_t> own(ctx, d_bases_out ? 0 : WE_WIN * 96);
+  uint32_t* bases = d_bases_out ? d_bases_out : own.p;
   KB_LAUNCH(ctx, gt_window_bases_kernel, 1, 32, 0, d_a, bases);
   KB_LAUNCH(ctx, gt_table_fill_kernel, cdiv(WE_WIN * WE_ENT, 128), 128, 0, bases, d_tab);
+}
+// bases1[w] = bases[w] * conj(gT^(2^(8w))): the window bases of A' = A / gT from those of A and the SRS-constant gT table
+// (entry (w, digit 1) of the 8-bit table is gT^(2^(8w)); gT is unitary, so the conjugate is the inverse) - 32 independent
+// Fq12 products instead of a second chain of 248 dependent cyclotomic squarings
+__global__ void gt_bases_div_gen_kernel(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ gt_tab, uint32_t* __restrict__ bases1) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= WE_WIN) return;
+  st_fq12(bases1 + 96 * w, ld_fq12(bases + 96 * w) * conj(ld_fq12(gt_tab + 96 * ((size_t)w * WE_ENT))));
 }
 
 void we_init_tables(kb_ctx* ctx) {
@@ -164,7 +164,7 @@ void we_init_tables(kb_ctx* ctx) {
   KB_CUDA(cudaMalloc((void**)&ctx->d_gt_tab16, GT_TAB16_LIMBS * 4));
   build_g2_table(ctx, g2, ctx->d_g2_tab);
   build_g2_table16(ctx, ctx->d_g2_tab, ctx->d_g2_tab16);
-  KB_LAUNCH(ctx, pairing_with_g2gen_kernel, 1, 32, 0, g1, 0u, g2, gt);
+  st_pairing_launch(ctx, g1, nullptr, g2, nullptr, 1, 2, gt, nullptr, nullptr, nullptr);
   build_gt_table(ctx, gt, ctx->d_gt_tab);
   KB_LAUNCH(ctx, gt_table16_kernel, cdiv((uint64_t)WE_WIN16 * WE_ENT16, 128), 128, 0, ctx->d_gt_tab, ctx->d_gt_tab16);
   KB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -256,12 +256,6 @@ __global__ void __launch_bounds__(128, 3) encrypt_ct_kernel(const uint32_t* __re
   ct_inf[i] = acc.is_inf() ? 1 : 0;
 }
 
-// a1 = a * conj(gT)  (gT is unitary: the conjugate is the inverse), gT = entry (window 0, digit 1) of its table
-__global__ void gt_div_gen_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ gt_tab, uint32_t* __restrict__ a1) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  st_fq12(a1, ld_fq12(a) * conj(ld_fq12(gt_tab)));
-}
-
 void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const uint32_t* d_points, const uint32_t* d_values,
                    const uint32_t* d_r, const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n,
                    uint32_t* d_ct, uint8_t* d_ct_inf, uint8_t* d_msg_ct) {
@@ -274,11 +268,12 @@ void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const
     DevBuf<uint32_t> com(ctx, 16), g2(ctx, 32), a(ctx, 96);
     KB_CUDA(cudaMemcpyAsync(com, key, 64, cudaMemcpyHostToDevice, ctx->stream));
     KB_CUDA(cudaMemcpyAsync(g2, consts::G2_GEN, 128, cudaMemcpyHostToDevice, ctx->stream));
-    KB_LAUNCH(ctx, pairing_with_g2gen_kernel, 1, 32, 0, com, key[16], g2, a);
-    build_gt_table(ctx, a, ctx->d_com_tab);
-    DevBuf<uint32_t> a1(ctx, 96);
-    KB_LAUNCH(ctx, gt_div_gen_kernel, 1, 32, 0, a.p, ctx->d_gt_tab, a1.p);
-    build_gt_table(ctx, a1, ctx->d_com1_tab);
+    // A = e(com, G2): one pairing on the compiled kernel (a lone warp: the latency of one dependent chain, 11 ms)
+    st_pairing_launch(ctx, com, nullptr, g2, nullptr, 1, 2, a, nullptr, nullptr, nullptr);
+    DevBuf<uint32_t> bases(ctx, WE_WIN * 96), bases1(ctx, WE_WIN * 96);
+    build_gt_table(ctx, a, ctx->d_com_tab, bases.p);
+    KB_LAUNCH(ctx, gt_bases_div_gen_kernel, 1, 32, 0, bases.p, ctx->d_gt_tab, bases1.p);
+    KB_LAUNCH(ctx, gt_table_fill_kernel, cdiv(WE_WIN * WE_ENT, 128), 128, 0, bases1.p, ctx->d_com1_tab);
     memcpy(ctx->com_cached, key, sizeof(key));
     ctx->com_tab_valid = true;
     ctx->com_tab16_valid = false;

@@ -25,7 +25,7 @@ for c in cs:
     else:
         os.environ.pop("KB_MSM_C", None)
     ctx = _ffi.Context(0)
-    ctx.srs_generate(a[0], n, download=False)
+    ctx.srs_generate(a[0], max(n, 1 << int(os.environ.get('SWEEP_SRS_LOG', '0'))), download=False)
     d = torch.from_numpy(a).cuda()
     for _ in range(4):
         out = ctx.msm_g1(d, n=n)
