@@ -1,6 +1,7 @@
-"""Small pass over every entry point for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): MSM at three window widths
-(two-digit reduction, quad-cooperative tail), open-all, encrypt (both per-commitment tables), decrypt on the pairing VM,
-verify, wire format."""
+"""Small pass over every entry point for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): MSM at both window
+widths (two-digit reduction, quad-cooperative tail) incl. the over-full-bucket path (all-equal scalars), SRS validation,
+open-all, encrypt (fresh commitment: the per-commitment pairing and tables), decrypt on the compiled pairing kernel and on
+the pairing VM, verify, wire format."""
 import sys
 sys.path.insert(0, ".")
 import numpy as np
@@ -19,6 +20,9 @@ tau = 0x1234567 % R
 ctx.srs_generate(fr_to_limbs(tau), 1 << 14, download=False)
 for n in (100, 5000, 1 << 14):
     xy, inf = ctx.msm_g1(rnd(n))
+same = np.ascontiguousarray(np.tile(fr_to_limbs(0x1234567890ABCDEF1234567890ABCDEF % R), (1 << 12, 1)))
+xy, inf = ctx.msm_g1(same)          # every window lands in one bucket: segments + both folds
+ctx.srs_validate()
 coeffs = rnd(64)
 com, ci = ctx.msm_g1(coeffs)
 proofs, pinf = ctx.open_all_fk(coeffs)
@@ -28,6 +32,13 @@ msgs = rng.integers(0, 256, size=n * 32, dtype=np.uint8); off = np.arange(n + 1,
 pts = rnd(n)
 ct, cti, mc = ctx.encrypt_batch(com, ci, pts, vals, rnd(n), msgs, off)
 out = ctx.decrypt_batch(proofs, pinf, ct, cti, mc, off)
+assert bytes(out[: n * 32]) != b"" 
+import os
+os.environ["KB_PAIRING_IMPL"] = "vm"
+vm_ctx = _ffi.Context(0)
+out_vm = vm_ctx.decrypt_batch(proofs, pinf, ct, cti, mc, off)
+assert np.array_equal(out, out_vm)
+vm_ctx.close()
 ok = ctx.verify_batch(np.tile(com, (n, 1)), np.zeros(n, np.uint8), pts, vals, proofs, pinf)
 b = ctx.g2_serialize(ct, cti, True)
 back = ctx.g2_deserialize(b, True, True)
