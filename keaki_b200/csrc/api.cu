@@ -94,6 +94,8 @@ int32_t kb_ctx_create(int32_t device, kb_ctx** out) {
 
 void kb_ctx_destroy(kb_ctx* ctx) {
   if (!ctx) return;
+  for (DeviceWorker* w : ctx->workers) delete w;
+  ctx->workers.clear();
   for (kb_ctx* p : ctx->peers) kb_ctx_destroy(p);
   ctx->peers.clear();
   cudaSetDevice(ctx->device);
@@ -378,10 +380,9 @@ template <class F>
 int32_t on_all_devices(kb_ctx* ctx, F f) {   // f(k, sub-context) on one host thread per device; first failure wins
   const size_t nd = 1 + ctx->peers.size();
   std::vector<int32_t> rc(nd, KB_OK);
-  std::vector<std::thread> th;
-  for (size_t k = 1; k < nd; k++) th.emplace_back([&rc, &f, ctx, k] { rc[k] = f(k, ctx->peers[k - 1]); });
+  for (size_t k = 1; k < nd; k++) ctx->workers[k - 1]->post([&rc, &f, ctx, k] { rc[k] = f(k, ctx->peers[k - 1]); });
   rc[0] = f(0, ctx);
-  for (auto& t : th) t.join();
+  for (size_t k = 1; k < nd; k++) ctx->workers[k - 1]->wait();
   for (int i = 0; i < KB_T_COUNT; i++)
     for (kb_ctx* p : ctx->peers) if (p->last_ms[i] > ctx->last_ms[i]) ctx->last_ms[i] = p->last_ms[i];   // the slowest device
   for (size_t k = 1; k < nd; k++)
@@ -423,6 +424,7 @@ int32_t kb_ctx_create_multi(const int32_t* devices, int32_t ndev, kb_ctx** out) 
     }
   }
   subs[0]->peers.assign(subs.begin() + 1, subs.end());
+  for (int k = 1; k < ndev; k++) subs[0]->workers.push_back(new DeviceWorker());
   *out = subs[0];
   return KB_OK;
 }

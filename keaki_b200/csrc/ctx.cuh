@@ -2,7 +2,11 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include <stdexcept>
 #include "../../include/keaki_b200.h"
@@ -25,6 +29,45 @@ struct MsmTable { int c = 0, nwin = 0; uint64_t n = 0; uint32_t* d = nullptr; };
 
 enum { KB_T_TOTAL = 0, KB_T_MSM_ACC = 1, KB_T_PAIRING = 2, KB_T_ENCRYPT = 3, KB_T_COUNT = 4 };
 
+// One host thread per peer device of a multi-device context, alive for the life of the context: a sharded call posts one
+// job per device and waits for all of them (no thread creation on the hot path).
+class DeviceWorker {
+ public:
+  DeviceWorker() : th_([this] { loop(); }) {}
+  ~DeviceWorker() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+    cv_.notify_all();
+    th_.join();
+  }
+  void post(std::function<void()> job) {
+    { std::lock_guard<std::mutex> l(m_); job_ = std::move(job); busy_ = true; }
+    cv_.notify_all();
+  }
+  void wait() { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [this] { return !busy_; }); }
+
+ private:
+  void loop() {
+    for (;;) {
+      std::function<void()> job;
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [this] { return stop_ || (busy_ && job_); });
+        if (stop_) return;
+        job = std::move(job_);
+        job_ = nullptr;
+      }
+      job();
+      { std::lock_guard<std::mutex> l(m_); busy_ = false; }
+      cv_.notify_all();
+    }
+  }
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::function<void()> job_;
+  bool busy_ = false, stop_ = false;
+  std::thread th_;
+};
+
 }  // namespace kb
 
 struct kb_ctx {
@@ -38,6 +81,7 @@ struct kb_ctx {
   int sm_count = 148;
   // multi-device context (kb_ctx_create_multi): this is the first device, `peers` are the contexts of the others
   std::vector<kb_ctx*> peers;
+  std::vector<kb::DeviceWorker*> workers;   // one per peer
   bool peer_access = true;
 
   // SRS (affine, Montgomery), resident for the life of the context

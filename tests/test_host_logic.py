@@ -141,3 +141,25 @@ def test_commit_size_check_happens_before_any_gpu_work():
         kzg.commit(setup, [1, 3, 2, 4])
     assert "PolynomialTooLarge(4, 2)" in str(e.value)
     assert kzg._strip([1, 2, 0, 0]) == [1, 2] and kzg._strip([0, 0]) == []
+
+
+def test_bench_helpers_sharded_trapdoor_traffic_and_scalars():
+    """bench.py's host logic: the combined-commitment check of the N > 1 step (each rank Horner-sums its slice, rank 0
+    weighs the parts with tau^(rank n)), the DRAM-traffic reader of the committed ncu export, uniform-below-r scalars"""
+    import bench
+    nrng = np.random.default_rng(5)
+    tau = 0x1234567890ABCDEF % FR_MODULUS
+    world, n = 3, 40
+    limbs = bench.rand_fr_limbs(nrng, world * n)
+    vals = fr_list(limbs)
+    assert all(0 <= v < FR_MODULUS for v in vals) and limbs.shape == (world * n, 8)
+    whole = sum(v * pow(tau, i, FR_MODULUS) for i, v in enumerate(vals)) % FR_MODULUS
+    parts = [bench.horner_mod_r(limbs[k * n:(k + 1) * n], tau, FR_MODULUS) for k in range(world)]
+    assert sum(p * pow(tau, k * n, FR_MODULUS) for k, p in enumerate(parts)) % FR_MODULUS == whole
+    assert bench.horner_mod_r(limbs, tau, FR_MODULUS) == whole
+    # top limbs reach above 2^252 (round 1 drew below 2^252, which hides the real top-window distribution of the MSM)
+    big = bench.rand_fr_limbs(nrng, 4000)
+    assert (big[:, 7] >= 0x10000000).mean() > 0.5 and (big[:, 7] <= 0x30644e72).all()
+    traffic, src = bench.ncu_dram_traffic("ncu_msm_accumulate_r02_raw.csv", "msm_accumulate_kernel")
+    assert src == "profiles/ncu_msm_accumulate_r02_raw.csv" and 1.0e9 < traffic < 3.0e9
+    assert bench.ncu_dram_traffic("missing.csv", "x") == (None, None)
