@@ -76,6 +76,7 @@ int32_t kb_ctx_create(int32_t device, kb_ctx** out) {
     for (auto& e : ctx->ev) KB_CUDA(cudaEventCreate(&e));
     we_upload_consts();
     wire_upload_consts();
+    wp_init(ctx);
     st_init(ctx);   // before the WE tables: gT = e(G1, G2) is computed by the compiled pairing kernel
     we_init_tables(ctx);
     vm_init(ctx);
@@ -105,6 +106,7 @@ void kb_ctx_destroy(kb_ctx* ctx) {
   we_free(ctx);
   vm_free(ctx);
   st_free(ctx);
+  wp_free(ctx);
   if (ctx->d_srs) cudaFree(ctx->d_srs);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->ev_copy) if (e) cudaEventDestroy(e);

@@ -114,6 +114,12 @@ struct kb_ctx {
   uint32_t* d_st_consts = nullptr;
   int st_shape = 0;
   int pairing_impl = 1;              // 0 = pairing VM (two lanes + interpreter), 1 = compiled single-thread kernel; KB_PAIRING_IMPL=vm|st
+  // warp-cooperative pairing (pairing_warp.cu): dense step descriptors of the two schedules (pairing, GT window bases),
+  // their output slots, the Fq2 constants; batches of at most wp_max_n pairings use it (KB_PAIRING_WARP_MAX, 0 = never)
+  uint32_t* d_wp_words[2] = {nullptr, nullptr};
+  uint16_t* d_wp_outs[2] = {nullptr, nullptr};
+  uint32_t* d_wp_consts = nullptr;
+  uint64_t wp_max_n = 0;
 
   // FK open-all cache: hat_s = DFT_2d(reversed SRS prefix) per d
   struct FkCache { uint64_t d = 0; uint32_t* d_hat_s = nullptr; };
@@ -241,6 +247,11 @@ void st_init(kb_ctx* ctx);                             // compiled pairing: cons
 void st_free(kb_ctx* ctx);
 void st_pairing_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf, uint64_t n,
                        int mode, uint32_t* d_gt, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out);
+void wp_init(kb_ctx* ctx);                             // warp-cooperative pairing: schedules upload (ctx creation)
+void wp_free(kb_ctx* ctx);
+void wp_pairing_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf, uint64_t n,
+                       int mode, uint32_t* d_gt, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out);
+void wp_gt_bases_launch(kb_ctx* ctx, const uint32_t* d_a, uint32_t* d_bases);   // bases[w] = a^(2^(8w)), w < 32
 void pairing_batch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
                    uint64_t n, uint8_t* d_gt_bytes);
 void decrypt_batch(kb_ctx* ctx, const uint32_t* d_proofs, const uint8_t* d_pinf, const uint32_t* d_ct, const uint8_t* d_cinf,

@@ -149,6 +149,8 @@ void st_free(kb_ctx* ctx) { cudaFree(ctx->d_st_consts); ctx->d_st_consts = nullp
 
 void st_pairing_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf, uint64_t n,
                        int mode, uint32_t* d_gt, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out) {
+  // small batches: one WARP per pairing (pairing_warp.cu) - a lone thread here needs 9 ms however few pairings there are
+  if (n <= ctx->wp_max_n) { wp_pairing_launch(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out); return; }
 #define KB_ST_GO(B, MB, NS) st_go<B, MB, NS>(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out)
   // Launch shape: 8 warps per SM at 255 registers (two blocks of 128) is the measured optimum on B200 (2^16 pairings:
   // 25.5 ms; 7 warps in one block 27.1, 6 warps 29.5, 12 warps at 168 registers 38.0, 16 warps at 128 registers 37.1 -

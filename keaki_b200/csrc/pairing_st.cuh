@@ -26,7 +26,7 @@ namespace kb {
 namespace st {
 
 #if defined(__CUDACC__)
-#define KB_ST_CALL __device__ __noinline__
+#define KB_ST_CALL static __device__ __noinline__
 #define KB_ST_INL __device__ __forceinline__
 #else
 #define KB_ST_CALL inline

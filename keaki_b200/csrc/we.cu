@@ -138,7 +138,8 @@ static void build_g2_table16(kb_ctx* ctx, const uint32_t* d_tab8, uint32_t* d_ta
 static void build_gt_table(kb_ctx* ctx, const uint32_t* d_a, uint32_t* d_tab, uint32_t* d_bases_out = nullptr) {
   DevBuf<uint32_t> own(ctx, d_bases_out ? 0 : WE_WIN * 96);
   uint32_t* bases = d_bases_out ? d_bases_out : own.p;
-  KB_LAUNCH(ctx, gt_window_bases_kernel, 1, 32, 0, d_a, bases);
+  if (ctx->wp_max_n) wp_gt_bases_launch(ctx, d_a, bases);   // the 248 dependent squarings, 9 products wide on one warp
+  else KB_LAUNCH(ctx, gt_window_bases_kernel, 1, 32, 0, d_a, bases);
   KB_LAUNCH(ctx, gt_table_fill_kernel, cdiv(WE_WIN * WE_ENT, 128), 128, 0, bases, d_tab);
 }
 // bases1[w] = bases[w] * conj(gT^(2^(8w))): the window bases of A' = A / gT from those of A and the SRS-constant gT table

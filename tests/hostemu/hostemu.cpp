@@ -17,6 +17,8 @@
 #include "../../keaki_b200/csrc/pairing_vm.cuh"
 #include "../../keaki_b200/csrc/pairing_prog_gen.cuh"
 #include "../../keaki_b200/csrc/pairing_st.cuh"
+#include "../../keaki_b200/csrc/pairing_warp.cuh"
+#include "../../keaki_b200/csrc/pairing_warp_gen.cuh"
 
 using namespace kb;
 
@@ -272,6 +274,45 @@ void he_st_f12_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   else st::f12inv(m);
   for (int i = 0; i < 6; i++) stq2(out + 16 * i, m.ld(st::F + i));
   delete s;
+}
+
+}  // extern "C"
+
+// The warp-cooperative pairing (pairing_warp.cuh): the shipped schedules run step by step, the 32 lanes of a step one
+// after the other - all of them compute (read) before any of them stores, as on the GPU.
+struct WpMem {
+  Fq2* s;
+  Fq2 ld(uint32_t a) const { return s[a]; }
+};
+
+extern "C" {
+
+// prog 0: pairing (inputs P, Qx, Qy, (xP, 0), (yP, 0)), 1: window bases of a GT table (input: a cyclotomic Fq12, tower order).
+// Inputs / outputs as 16 Montgomery limbs per Fq2.
+int he_wp_run(int prog, const uint32_t* inputs, uint32_t* outs) {
+  const wpprog::Program& p = prog == 0 ? wpprog::PAIRING : wpprog::GT_BASES;
+  std::vector<Fq2> slots(p.nslots, Fq2::zero());
+  for (int i = 0; i < p.ninputs; i++) slots[p.inputs[i]] = ldq2(inputs + 16 * i);
+  for (int i = 0; i < p.nconsts; i++) slots[p.const_slot[i]] = ldq2(wpprog::CONSTS + 16 * p.const_idx[i]);
+  WpMem m{slots.data()};
+  std::vector<uint32_t> words((size_t)p.nsteps * 32 * 8);
+  wpprog::expand(p, words.data());
+  for (int s = 0; s < p.nsteps; s++) {
+    Fq2 r[32];
+    for (int lane = 0; lane < 32; lane++) r[lane] = wp::lane_compute(m, words.data() + 8 * (32 * s + lane));
+    for (int lane = 0; lane < 32; lane++) {
+      const uint32_t w0 = words[8 * (32 * s + lane)];
+      if ((w0 >> 4) & 1u) slots[(w0 >> 8) & 511u] = r[lane];
+    }
+  }
+  for (int i = 0; i < p.nouts; i++) stq2(outs + 16 * i, slots[p.outs[i]]);
+  return p.nsteps;
+}
+// v9: 288-bit two's complement integer in (-128 q, 128 q)  ->  out8 = v mod q
+void he_wp_reduce9(const uint32_t* v9, uint32_t* out8) {
+  uint32_t v[9];
+  memcpy(v, v9, 36);
+  stq(out8, wp::reduce9(v));
 }
 
 }  // extern "C"
