@@ -162,7 +162,9 @@ uint64_t kb_launch_count(const kb_ctx* ctx);
 
 /* Device time in ms of the last call's dominant kernel(s), measured with CUDA events on the
  * context's stream: which = 0 total of all kernels of the last call, 1 = MSM bucket accumulation,
- * 2 = pairing kernel, 3 = encrypt kernel.  Negative if not recorded. */
+ * 2 = pairing kernel, 3 = encrypt kernel, 4 = per-commitment setup inside kb_encrypt_batch (the
+ * pairing e(com, G2), its window bases and the two power tables; -1 when the call reused the cached
+ * commitment).  Negative if not recorded. */
 float kb_last_kernel_ms(const kb_ctx* ctx, int32_t which);
 
 #ifdef __cplusplus

@@ -18,6 +18,7 @@ int32_t fail(kb_ctx* ctx, int32_t code, const std::string& msg) {
   if (!(ctx)) return KB_ERR_ARG;                   \
   try {                                            \
     KB_CUDA(cudaSetDevice((ctx)->device));         \
+    (ctx)->last_ms[KB_T_SETUP] = -1.f;             \
     timer_start((ctx), KB_T_TOTAL);
 
 #define KB_API_END(ctx)                                                   \

@@ -27,7 +27,7 @@ struct ApiError : std::runtime_error {
 // Fixed-base tables for the MSM over the SRS: tab[w * n + i] = 2^(c w) * g1[i], affine.
 struct MsmTable { int c = 0, nwin = 0; uint64_t n = 0; uint32_t* d = nullptr; };
 
-enum { KB_T_TOTAL = 0, KB_T_MSM_ACC = 1, KB_T_PAIRING = 2, KB_T_ENCRYPT = 3, KB_T_COUNT = 4 };
+enum { KB_T_TOTAL = 0, KB_T_MSM_ACC = 1, KB_T_PAIRING = 2, KB_T_ENCRYPT = 3, KB_T_SETUP = 4, KB_T_COUNT = 5 };
 
 // One host thread per peer device of a multi-device context, alive for the life of the context: a sharded call posts one
 // job per device and waits for all of them (no thread creation on the hot path).
@@ -126,7 +126,7 @@ struct kb_ctx {
   std::vector<FkCache> fk_cache;        // at most KB_FK_CACHE_MAX entries, oldest evicted (256 MiB per entry at d = 2^20)
 
   cudaEvent_t ev[2 * kb::KB_T_COUNT] = {};
-  float last_ms[kb::KB_T_COUNT] = {-1.f, -1.f, -1.f, -1.f};
+  float last_ms[kb::KB_T_COUNT] = {-1.f, -1.f, -1.f, -1.f, -1.f};
 };
 
 namespace kb {

@@ -30,6 +30,19 @@ struct WpDevMem {
     r.c1.v[4] = q3.x; r.c1.v[5] = q3.y; r.c1.v[6] = q3.z; r.c1.v[7] = q3.w;
     return r;
   }
+  __device__ __forceinline__ Fq ld_half(uint32_t a, uint32_t h) const {
+    const uint4* p = base + a + 2 * h * ns;
+    const uint4 q0 = p[0], q1 = p[ns];
+    Fq r;
+    r.v[0] = q0.x; r.v[1] = q0.y; r.v[2] = q0.z; r.v[3] = q0.w;
+    r.v[4] = q1.x; r.v[5] = q1.y; r.v[6] = q1.z; r.v[7] = q1.w;
+    return r;
+  }
+  __device__ __forceinline__ void st_half(uint32_t a, uint32_t h, const Fq& x) const {
+    uint4* p = base + a + 2 * h * ns;
+    p[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    p[ns] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+  }
   __device__ __forceinline__ void st(uint32_t a, const Fq2& x) const {
     uint4* p = base + a;
     p[0] = make_uint4(x.c0.v[0], x.c0.v[1], x.c0.v[2], x.c0.v[3]);
@@ -57,7 +70,7 @@ __device__ __forceinline__ void wp_run(const WpDevMem& m, const WpArgs& a, uint3
     if (s + 1 < a.nsteps) { d0 = dp[64 * (size_t)(s + 1)]; d1 = dp[64 * (size_t)(s + 1) + 1]; }   // next step's descriptor in flight
     const Fq2 r = wp::lane_compute(m, d);
     __syncwarp();
-    if ((d[0] >> 4) & 1u) m.st((d[0] >> 8) & 511u, r);
+    wp::lane_store(m, d, r);
     __syncwarp();
   }
 }
@@ -163,9 +176,9 @@ void wp_init(kb_ctx* ctx) {
     KB_CUDA(cudaMalloc((void**)&ctx->d_wp_outs[which], p.nouts * 2));
     KB_CUDA(cudaMemcpy(ctx->d_wp_outs[which], p.outs, p.nouts * 2, cudaMemcpyHostToDevice));
   }
-  // Batches up to this many pairings take the warp-cooperative kernel (the crossover with the
-  // one-thread-per-pairing kernel, whose latency floor is one lone warp's 9 ms)
-  ctx->wp_max_n = 2048;
+  // Batches up to this many pairings take the warp-cooperative kernel: measured crossover with the one-thread-per-pairing
+  // kernel, whose floor is a lone warp's 9.1 ms (4096 pairings: 6.0 ms here, 8192: 11.4)
+  ctx->wp_max_n = 6144;
   if (const char* e = getenv("KB_PAIRING_WARP_MAX")) ctx->wp_max_n = strtoull(e, nullptr, 10);
 }
 void wp_free(kb_ctx* ctx) {

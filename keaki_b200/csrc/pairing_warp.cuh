@@ -8,7 +8,8 @@
 // exactly one combination level separates two product levels, and list-schedules the DAG into STEPS of one kind:
 //   MUL   d = (a1 + a2) (b1 + b2)       lazily reduced Fq2 product (fpl.cuh); the a-side sum is not reduced
 //   LIN   d = sum c_i x_i + xi sum c'_j y_j   small signed integer coefficients: accumulated as 288-bit integers
-//                                       (one IMAD.WIDE row + one carry chain per term and coordinate), reduced ONCE
+//                                       (one IMAD.WIDE row + one carry chain per term), reduced ONCE; two lanes per
+//                                       node, one per coordinate of the Fq2 result
 //   CONJ  d = conj(x)        INV  d = 1 / x   (once per pairing, one lane)
 // Every lane reads its 32-byte descriptor (prefetched one step ahead), computes from the warp's slot file in shared
 // memory, and after a warp barrier stores its result, so results may reuse slots whose last reader is in the same step.
@@ -21,7 +22,6 @@ namespace kb {
 namespace wp {
 
 enum : uint32_t { K_NOP = 0, K_MUL = 1, K_LIN = 2, K_CONJ = 3, K_INV = 4 };
-static constexpr int MAX_TERMS = 14;
 
 // acc (288-bit two's complement) += (m ? -1 : 1) * c * x;  m = 0 or 0xffffffff
 KB_ST_INL void mac9(uint32_t* acc, const Fq& x, uint32_t c, uint32_t m) {
@@ -84,48 +84,40 @@ KB_ST_INL Fq reduce9(uint32_t* v) {
   return r;
 }
 
-KB_ST_INL uint32_t term_of(const uint32_t* d, int k) { return (d[1 + (k >> 1)] >> (16 * (k & 1))) & 0xffffu; }
-
+// One coordinate of a LIN node: lane `half` computes c_half of  sum c_i x_i + xi sum c'_j y_j, where
+// xi (y0 + y1 u) = (9 y0 - y1) + (9 y1 + y0) u.  The 14 16-bit terms sit in a 7-register queue that is shifted as they
+// are consumed, so that the (step-uniform) term counts drive two small loops instead of 28 unrolled bodies: the warp is
+// alone on its scheduler, and instruction fetch of a long straight-line body was a fifth of its stalls.
 template <class M>
-KB_ST_INL Fq2 lin(const M& m, const uint32_t* d, uint32_t nu, uint32_t nw) {
-  uint32_t u0[9], u1[9];
+KB_ST_INL Fq lin_half(const M& m, const uint32_t* d, uint32_t nu, uint32_t nw, uint32_t half) {
+  uint32_t acc[9];
 #pragma unroll
-  for (int i = 0; i < 9; i++) u0[i] = u1[i] = 0;
+  for (int i = 0; i < 9; i++) acc[i] = 0;
+  uint32_t q[7];
 #pragma unroll
-  for (int k = 0; k < MAX_TERMS; k++) {
-    if ((uint32_t)k < nu) {
-      const uint32_t tm = term_of(d, k);
-      const Fq2 x = m.ld(tm & 511u);
-      const uint32_t c = ((tm >> 10) & 63u) + 1u, neg = 0u - ((tm >> 9) & 1u);
-      mac9(u0, x.c0, c, neg);
-      mac9(u1, x.c1, c, neg);
-    }
+  for (int i = 0; i < 7; i++) q[i] = d[1 + i];
+#define KB_WP_NEXT_TERM(tm)                                                           \
+  const uint32_t tm = q[0] & 0xffffu;                                                 \
+  _Pragma("unroll") for (int i = 0; i < 6; i++) q[i] = (q[i] >> 16) | (q[i + 1] << 16); \
+  q[6] >>= 16;
+#pragma unroll 1
+  for (uint32_t k = 0; k < nu; k++) {
+    KB_WP_NEXT_TERM(tm)
+    mac9(acc, m.ld_half(tm & 511u, half), ((tm >> 10) & 63u) + 1u, 0u - ((tm >> 9) & 1u));
   }
-  if (nw) {
-    uint32_t w0[9], w1[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) w0[i] = w1[i] = 0;
-#pragma unroll
-    for (int k = 0; k < MAX_TERMS; k++) {
-      if ((uint32_t)k < nw) {
-        const uint32_t tm = term_of(d, MAX_TERMS - 1 - k);
-        const Fq2 x = m.ld(tm & 511u);
-        const uint32_t c = ((tm >> 10) & 63u) + 1u, neg = 0u - ((tm >> 9) & 1u);
-        mac9(w0, x.c0, c, neg);
-        mac9(w1, x.c1, c, neg);
-      }
-    }
-    // (9 + u)(w0 + w1 u) = (9 w0 - w1) + (9 w1 + w0) u
-    mad9x9(u0, w0); sub9(u0, w1);
-    mad9x9(u1, w1); add9(u1, w0);
+  const uint32_t flip = half ? 0u : 0xffffffffu;   // the cross term enters c0 with a minus sign
+#pragma unroll 1
+  for (uint32_t k = 0; k < nw; k++) {
+    KB_WP_NEXT_TERM(tm)
+    const uint32_t c = ((tm >> 10) & 63u) + 1u, neg = 0u - ((tm >> 9) & 1u);
+    mac9(acc, m.ld_half(tm & 511u, half), 9u * c, neg);
+    mac9(acc, m.ld_half(tm & 511u, half ^ 1u), c, neg ^ flip);
   }
-  Fq2 r;
-  r.c0 = reduce9(u0);
-  r.c1 = reduce9(u1);
-  return r;
+#undef KB_WP_NEXT_TERM
+  return reduce9(acc);
 }
 
-// One lane's share of a step: the value it will store (`dst`, when `active`).  Reads only.
+// One lane's share of a step: the value it will store (lane_store).  Reads only.
 template <class M>
 KB_ST_INL Fq2 lane_compute(const M& m, const uint32_t* d) {
   const uint32_t kind = d[0] & 15u, active = (d[0] >> 4) & 1u;
@@ -135,7 +127,7 @@ KB_ST_INL Fq2 lane_compute(const M& m, const uint32_t* d) {
     const Fq2 b = m.ld(d[2] & 0xffffu) + m.ld(d[2] >> 16);
     r = st::f2mul(a, b);
   } else if (kind == K_LIN) {
-    r = lin(m, d, (d[0] >> 20) & 15u, (d[0] >> 24) & 15u);
+    r.c0 = lin_half(m, d, (d[0] >> 20) & 15u, (d[0] >> 24) & 15u, (d[0] >> 17) & 1u);
   } else if (kind == K_CONJ) {
     r = m.ld(d[1] & 0xffffu);
     r.c1 = -r.c1;
@@ -143,6 +135,14 @@ KB_ST_INL Fq2 lane_compute(const M& m, const uint32_t* d) {
     if (active) r = st::f2inv(m.ld(d[1] & 0xffffu));
   }
   return r;
+}
+// ... and the store, after every lane of the step has computed
+template <class M>
+KB_ST_INL void lane_store(const M& m, const uint32_t* d, const Fq2& r) {
+  if (!((d[0] >> 4) & 1u)) return;
+  const uint32_t dst = (d[0] >> 8) & 511u;
+  if ((d[0] & 15u) == K_LIN) m.st_half(dst, (d[0] >> 17) & 1u, r.c0);
+  else m.st(dst, r);
 }
 
 }  // namespace wp

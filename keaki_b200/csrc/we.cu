@@ -127,6 +127,27 @@ __global__ void __launch_bounds__(128) gt_table_fill_kernel(const uint32_t* __re
   st_fq12(tab + 96 * (size_t)t, acc);
 }
 
+// both per-commitment tables in one launch: A (bases) and A' = A / gT, whose window bases are bases[w] * conj(gT^(2^(8w)))
+// (entry (w, digit 1) of the SRS-constant 8-bit gT table; gT is unitary, so the conjugate is the inverse) - 32 independent
+// Fq12 products instead of a second chain of 248 dependent squarings, folded into the fill
+__global__ void __launch_bounds__(128) gt_table_fill2_kernel(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ gt_tab,
+                                                             uint32_t* __restrict__ tab_a, uint32_t* __restrict__ tab_a1) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * WE_WIN * WE_ENT) return;
+  const bool second = t >= WE_WIN * WE_ENT;
+  if (second) t -= WE_WIN * WE_ENT;
+  const uint32_t w = t / WE_ENT, d = t % WE_ENT + 1;
+  Fq12 b = ld_fq12(bases + 96 * w);
+  if (second) b = b * conj(ld_fq12(gt_tab + 96 * ((size_t)w * WE_ENT)));
+  Fq12 acc = b;
+  const int top = 31 - __clz(d);
+  for (int bit = top - 1; bit >= 0; bit--) {
+    acc = cyclotomic_sqr(acc);
+    if ((d >> bit) & 1u) acc = acc * b;
+  }
+  st_fq12((second ? tab_a1 : tab_a) + 96 * (size_t)t, acc);
+}
+
 static void build_g2_table(kb_ctx* ctx, const uint32_t* d_base_xy, uint32_t* d_tab) {
   DevBuf<uint32_t> bases(ctx, WE_WIN * 64);
   KB_LAUNCH(ctx, g2_window_bases_kernel, 1, 32, 0, d_base_xy, bases);
@@ -135,22 +156,12 @@ static void build_g2_table(kb_ctx* ctx, const uint32_t* d_base_xy, uint32_t* d_t
 static void build_g2_table16(kb_ctx* ctx, const uint32_t* d_tab8, uint32_t* d_tab16) {
   KB_LAUNCH(ctx, g2_table16_kernel, cdiv((uint64_t)WE_WIN16 * WE_ENT16, 128), 128, 0, d_tab8, d_tab16);
 }
-static void build_gt_table(kb_ctx* ctx, const uint32_t* d_a, uint32_t* d_tab, uint32_t* d_bases_out = nullptr) {
-  DevBuf<uint32_t> own(ctx, d_bases_out ? 0 : WE_WIN * 96);
-  uint32_t* bases = d_bases_out ? d_bases_out : own.p;
+static void build_gt_table(kb_ctx* ctx, const uint32_t* d_a, uint32_t* d_tab) {
+  DevBuf<uint32_t> bases(ctx, WE_WIN * 96);
   if (ctx->wp_max_n) wp_gt_bases_launch(ctx, d_a, bases);   // the 248 dependent squarings, 9 products wide on one warp
   else KB_LAUNCH(ctx, gt_window_bases_kernel, 1, 32, 0, d_a, bases);
   KB_LAUNCH(ctx, gt_table_fill_kernel, cdiv(WE_WIN * WE_ENT, 128), 128, 0, bases, d_tab);
 }
-// bases1[w] = bases[w] * conj(gT^(2^(8w))): the window bases of A' = A / gT from those of A and the SRS-constant gT table
-// (entry (w, digit 1) of the 8-bit table is gT^(2^(8w)); gT is unitary, so the conjugate is the inverse) - 32 independent
-// Fq12 products instead of a second chain of 248 dependent cyclotomic squarings
-__global__ void gt_bases_div_gen_kernel(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ gt_tab, uint32_t* __restrict__ bases1) {
-  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= WE_WIN) return;
-  st_fq12(bases1 + 96 * w, ld_fq12(bases + 96 * w) * conj(ld_fq12(gt_tab + 96 * ((size_t)w * WE_ENT))));
-}
-
 void we_init_tables(kb_ctx* ctx) {
   KB_CUDA(cudaMalloc((void**)&ctx->d_g2_tab, G2_TAB_LIMBS * 4));
   KB_CUDA(cudaMalloc((void**)&ctx->d_tau2_tab, G2_TAB_LIMBS * 4));
@@ -269,19 +280,25 @@ void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const
     DevBuf<uint32_t> com(ctx, 16), g2(ctx, 32), a(ctx, 96);
     KB_CUDA(cudaMemcpyAsync(com, key, 64, cudaMemcpyHostToDevice, ctx->stream));
     KB_CUDA(cudaMemcpyAsync(g2, consts::G2_GEN, 128, cudaMemcpyHostToDevice, ctx->stream));
-    // A = e(com, G2): one pairing on the compiled kernel (a lone warp: the latency of one dependent chain, 11 ms)
+    // A = e(com, G2): one pairing (warp-cooperative kernel: 1.4 ms; a lone thread of the batch kernel needs 9), the 248
+    // dependent squarings of its window bases on one warp, then both power tables in one launch
+    timer_start(ctx, KB_T_SETUP);
     st_pairing_launch(ctx, com, nullptr, g2, nullptr, 1, 2, a, nullptr, nullptr, nullptr);
-    DevBuf<uint32_t> bases(ctx, WE_WIN * 96), bases1(ctx, WE_WIN * 96);
-    build_gt_table(ctx, a, ctx->d_com_tab, bases.p);
-    KB_LAUNCH(ctx, gt_bases_div_gen_kernel, 1, 32, 0, bases.p, ctx->d_gt_tab, bases1.p);
-    KB_LAUNCH(ctx, gt_table_fill_kernel, cdiv(WE_WIN * WE_ENT, 128), 128, 0, bases1.p, ctx->d_com1_tab);
+    DevBuf<uint32_t> bases(ctx, WE_WIN * 96);
+    if (ctx->wp_max_n) wp_gt_bases_launch(ctx, a, bases.p);
+    else KB_LAUNCH(ctx, gt_window_bases_kernel, 1, 32, 0, a.p, bases.p);
+    KB_LAUNCH(ctx, gt_table_fill2_kernel, cdiv(2 * WE_WIN * WE_ENT, 128), 128, 0, bases.p, ctx->d_gt_tab, ctx->d_com_tab, ctx->d_com1_tab);
+    timer_stop(ctx, KB_T_SETUP);
     memcpy(ctx->com_cached, key, sizeof(key));
     ctx->com_tab_valid = true;
     ctx->com_tab16_valid = false;
     ctx->com_msgs = 0;
   }
   if (!n) return;
-  if (!ctx->com_tab16_valid && ctx->com_msgs >= (1ull << 15)) {
+  // 16-bit tables halve the products per message and cost 2^20 products each to build: they are bought once the messages
+  // already encrypted under this commitment would have paid for them (2 * 2^20 / 32 = 2^16: the ski-rental rule, at most
+  // twice the cost of knowing the future)
+  if (!ctx->com_tab16_valid && ctx->com_msgs >= (1ull << 16)) {
     if (!ctx->d_com_tab16) KB_CUDA(cudaMalloc((void**)&ctx->d_com_tab16, GT_TAB16_LIMBS * 4));
     KB_LAUNCH(ctx, gt_table16_kernel, cdiv((uint64_t)WE_WIN16 * WE_ENT16, 128), 128, 0, ctx->d_com_tab, ctx->d_com_tab16);
     if (!ctx->d_com1_tab16) KB_CUDA(cudaMalloc((void**)&ctx->d_com1_tab16, GT_TAB16_LIMBS * 4));

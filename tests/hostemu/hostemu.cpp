@@ -283,6 +283,9 @@ void he_st_f12_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
 struct WpMem {
   Fq2* s;
   Fq2 ld(uint32_t a) const { return s[a]; }
+  Fq ld_half(uint32_t a, uint32_t h) const { return h ? s[a].c1 : s[a].c0; }
+  void st(uint32_t a, const Fq2& v) const { s[a] = v; }
+  void st_half(uint32_t a, uint32_t h, const Fq& v) const { if (h) s[a].c1 = v; else s[a].c0 = v; }
 };
 
 extern "C" {
@@ -300,10 +303,7 @@ int he_wp_run(int prog, const uint32_t* inputs, uint32_t* outs) {
   for (int s = 0; s < p.nsteps; s++) {
     Fq2 r[32];
     for (int lane = 0; lane < 32; lane++) r[lane] = wp::lane_compute(m, words.data() + 8 * (32 * s + lane));
-    for (int lane = 0; lane < 32; lane++) {
-      const uint32_t w0 = words[8 * (32 * s + lane)];
-      if ((w0 >> 4) & 1u) slots[(w0 >> 8) & 511u] = r[lane];
-    }
+    for (int lane = 0; lane < 32; lane++) wp::lane_store(m, words.data() + 8 * (32 * s + lane), r[lane]);
   }
   for (int i = 0; i < p.nouts; i++) stq2(outs + 16 * i, slots[p.outs[i]]);
   return p.nsteps;

@@ -135,15 +135,18 @@ class EV:
             a0, b0 = terms.get(d, (0, 0))
             terms[d] = (a0 + ha, b0 + hb)
             terms = {k: c for k, c in terms.items() if c != (0, 0)}
-        while _nunits(terms) > MAX_TERMS:
-            # split: materialise the heaviest prefix that fits, keep going with it as one term
-            part, n = {}, 0
-            for v, c in sorted(terms.items(), key=lambda kv: -((kv[1][0] != 0) + (kv[1][1] != 0))):
+        def weight(c):
+            return abs(c[0]) + 10 * abs(c[1])
+        while _nunits(terms) > MAX_TERMS or sum(weight(c) for c in terms.values()) > LIN_BOUND:
+            # split: materialise the heaviest part that fits one descriptor, keep going with it as one term
+            part, n, wsum = {}, 0, 0
+            for v, c in sorted(terms.items(), key=lambda kv: -weight(kv[1])):
                 k = (c[0] != 0) + (c[1] != 0)
-                if n + k <= MAX_TERMS:
+                if n + k <= MAX_TERMS and wsum + weight(c) <= LIN_BOUND:
                     part[v] = c
                     n += k
-            assert len(part) >= 2 or n >= 2
+                    wsum += weight(c)
+            assert wsum >= 2
             for v in part:
                 del terms[v]
             u, w = _units(part)
@@ -234,6 +237,7 @@ class EV:
 
 
 FOLD_SUMS = True
+SHALLOW = True        # depth-1 Fq12 routines and the shallow point chain (below)
 ZERO_VID = -1   # "the zero slot" inside MUL sources
 
 
@@ -250,18 +254,113 @@ def _zero_value(t):
     return EV(t, {})
 
 
+# ---------------------------------------------------------------------------------------------
+# Miller loop with a SHALLOW point chain.  The G2 accumulator T is independent of f, and with the Jacobian formulas of
+# gen_pairing_prog.py its dependent chain (3 product levels per doubling, 5 per addition: 372 levels) is what bounds the
+# Miller loop of a lane-parallel schedule, not the 156 levels of f.  Homogeneous projective coordinates on the twist
+# y^2 = x^3 + b' (b' = 3 / xi) as in arkworks' own BN `doubling_step` / `addition_step` (ark-ec 0.4.2 models/bn/g2.rs),
+# rearranged for depth: T = (X, Y, Z, Zb = b' Z); doubling in 2 levels (11 products), mixed addition in 3 (20 products).
+# Line functions differ from the Jacobian ones by factors in Fq2, which the final exponentiation kills: GT is the same.
+# ---------------------------------------------------------------------------------------------
+C_TWIST_B = len(gp.CONSTS)                                   # index in WP_CONSTS
+WP_CONSTS = list(gp.CONSTS) + [gp.f2_mul((3, 0), gp.f2_inv(gp.XI))]
+WP_CONST_NAMES = list(gp.CONST_NAMES) + ["twist_b"]
+
+
+def proj_dbl(T):
+    """2 T and the tangent line (l0, l1, l3): l0 yP + l1 xP w + l3 w^3"""
+    X, Y, Z, Zb = T
+    xy, b, c, yz, yzb, j = X * Y, Y.sqr(), Z * Zb, Y * Z, Y * Zb, X.sqr()     # c = b' Z^2
+    e = c.tpl()                     # 3 b' Z^2
+    f = e.tpl()
+    h = yz.dbl()                    # 2 Y Z
+    g = b + f
+    x3 = (xy * (b - f)).dbl()       # 4 x arkworks' (X3, Y3, Z3): a = XY/2, g = (b + f)/2
+    y3 = g.sqr() - e.sqr().scale(12)
+    z3 = (b * h).scale(4)
+    zb3 = (b * yzb).scale(8)
+    return (h, -j.tpl(), b - e), (x3, y3, z3, zb3)
+
+
+def proj_add(T, x2, y2):
+    """T + Q for affine Q = (x2, y2), and the chord line"""
+    X, Y, Z, Zb = T
+    theta = Y - y2 * Z
+    lam = X - x2 * Z
+    c, d = theta.sqr(), lam.sqr()
+    zl, xl, tx, tl, tz, yl, zbl = Z * lam, X * lam, theta * X, theta * lam, theta * Z, Y * lam, Zb * lam
+    jj = theta * x2 - lam * y2
+    x3 = d.sqr() + zl * c - (xl * d).dbl()                 # lam (lam^3 + Z theta^2 - 2 X lam^2)
+    y3 = (tx.tpl() - tl - yl) * d - tz * c                 # theta (3 X lam^2 - lam^3 - Z theta^2) - Y lam^3
+    z3 = zl * d
+    zb3 = zbl * d
+    return (lam, -theta, jj), (x3, y3, z3, zb3)
+
+
+def miller_shallow(t, P, Qx, Qy):
+    one, bt = _const(t, gp.C_ONE), _const(t, C_TWIST_B)
+    T = (Qx, Qy, one, bt)
+    nQy = -Qy
+    f = None
+    for i in range(63, -1, -1):
+        line, T = proj_dbl(T)
+        if f is None:
+            zero = EV(t, {})
+            f = [line[0].mulfq(P, 1), line[1].mulfq(P, 0), zero, line[2], zero, zero]
+        else:
+            f = gp.apply_line(gp.f12_sqr(f), line, P)
+        dgt = gp.ATE[i]
+        if dgt:
+            line, T = proj_add(T, Qx, Qy if dgt > 0 else nQy)
+            f = gp.apply_line(f, line, P)
+    twx, twy = _const(t, gp.C_TWX), _const(t, gp.C_TWY)
+    q1x, q1y = Qx.conj() * twx, Qy.conj() * twy
+    q2x, q2y = q1x.conj() * twx, -(q1y.conj() * twy)
+    line, T = proj_add(T, q1x, q1y)
+    f = gp.apply_line(f, line, P)
+    line, T = proj_add(T, q2x, q2y)
+    f = gp.apply_line(f, line, P)
+    return f
+
+
+# Fq12 routines with ONE product level and no combination level in front of it: every product operand is a materialised
+# value or the plain sum of two (folded into the product step).  They spend products (idle lanes) to save depth: 18 instead
+# of 12 for the square, 16 instead of 13 for the sparse product, 24 instead of 18 for the full product.
+def f12_sqr_shallow(a):
+    a0, a1 = gp.halves(a)
+    s0, s1, m = gp.f6_mul(a0, a0), gp.f6_mul(a1, a1), gp.f6_mul(a0, a1)
+    return gp.from_halves(gp.f6_add(s0, gp.f6_mul_v(s1)), gp.f6_add(m, m))
+
+
+def f12_mul_shallow(a, b):
+    a0, a1 = gp.halves(a)
+    b0, b1 = gp.halves(b)
+    c0 = gp.f6_add(gp.f6_mul(a0, b0), gp.f6_mul_v(gp.f6_mul(a1, b1)))
+    c1 = gp.f6_add(gp.f6_mul(a0, b1), gp.f6_mul(a1, b0))
+    return gp.from_halves(c0, c1)
+
+
+def mul_by_line_shallow(f, l0, l1, l3):
+    f0, f1 = gp.halves(f)
+    c0 = gp.f6_add(gp.f6_mul_f2(f0, l0), gp.f6_mul_v(gp.f6_mul_01(f1, l1, l3)))
+    c1 = gp.f6_add(gp.f6_mul_01(f0, l1, l3), gp.f6_mul_f2(f1, l0))
+    return gp.from_halves(c0, c1)
+
+
 def trace(what):
     """what: "pairing" (inputs P, Qx, Qy and the split coordinates (xP, 0), (yP, 0); outputs GT in tower order) or
     "gt_bases" (input: a cyclotomic Fq12 in tower order; outputs a^(2^(8 w)), w = 0..31, tower order each)."""
     t = WTrace()
-    saved = (gp.const, gp.zero_value, gp.USE_MACROS)
+    saved = (gp.const, gp.zero_value, gp.USE_MACROS, gp.f12_sqr, gp.f12_mul, gp.mul_by_line)
     gp.const, gp.zero_value, gp.USE_MACROS = _const, _zero_value, False
+    if SHALLOW:
+        gp.f12_sqr, gp.f12_mul, gp.mul_by_line = f12_sqr_shallow, f12_mul_shallow, mul_by_line_shallow
     try:
         if what == "pairing":
             p, qx, qy = t.new_input(), t.new_input(), t.new_input()
             xp, yp = t.new_input(), t.new_input()
             t.split = {(p, 0): xp, (p, 1): yp}
-            f = gp.miller(t, EV.of(t, p), EV.of(t, qx), EV.of(t, qy))
+            f = miller_shallow(t, EV.of(t, p), EV.of(t, qx), EV.of(t, qy))
             f = gp.final_exp(t, f)
             c0, c1 = gp.halves(f)
             outs = list(c0 + c1)
@@ -278,7 +377,7 @@ def trace(what):
                     for _ in range(8):
                         g = gp.cyclotomic_sqr(g)
     finally:
-        gp.const, gp.zero_value, gp.USE_MACROS = saved
+        gp.const, gp.zero_value, gp.USE_MACROS, gp.f12_sqr, gp.f12_mul, gp.mul_by_line = saved
     t.outputs = []
     for x in outs:
         if x.is_zero():
@@ -295,7 +394,7 @@ def trace(what):
 # scheduling and slot allocation
 # ---------------------------------------------------------------------------------------------
 def lin_cost(nu, nw):
-    return 120 + 60 * (nu + nw) + (330 if nw else 200)
+    return 150 + 40 * nu + 75 * nw + 110
 
 
 def schedule(t):
@@ -359,7 +458,7 @@ def schedule(t):
                 nu2, nw2 = max(mu, len(nd.u)), max(mw, len(nd.w))
                 # open a new step when the descriptor would overflow, the step is full, or when mixing would cost more
                 # than a second step
-                split = len(cur) == LANES or nu2 + nw2 > MAX_TERMS
+                split = len(cur) == LANES // 2 or nu2 + nw2 > MAX_TERMS
                 if cur and not split and lin_cost(nu2, nw2) > lin_cost(mu, mw) + 400 and len(group) > LANES // 2:
                     split = True
                 if split:
@@ -420,10 +519,11 @@ def allocate(t, steps, users, live):
 
 def build(what):
     """descriptor words, 8 x u32 per lane per step:
-         w0 = kind | active << 4 | dst << 8 | nU << 20 | nW << 24   (nU, nW: the step's loop bounds, same in all lanes)
+         w0 = kind | active << 4 | dst << 8 | half << 17 | nU << 20 | nW << 24   (nU, nW: the step's loop bounds, same in
+              all lanes; half: a LIN node occupies two adjacent lanes, lane `half` computes coordinate c_half of the result)
          MUL: w1 = a1 | a2 << 16, w2 = b1 | b2 << 16:  d = (a1 + a2) * (b1 + b2), the a-side sum not reduced
          LIN: terms t0..t13 of 16 bits (slot | sign << 9 | (|c| - 1) << 10), two per word in w1..w7; t0..t(nU-1) are the
-              plain terms, t13, t12 .. t(14-nW) the terms multiplied by xi; absent terms name the zero slot (coefficient 1).
+              plain terms, the next nW the terms multiplied by xi; absent terms name the zero slot (coefficient 1).
               The integer value sum |c_u| + 10 sum |c_w| stays below LIN_BOUND (the kernel adds 128 q before reducing)
          CONJ / INV: w1 = source slot"""
     t = trace(what)
@@ -440,25 +540,29 @@ def build(what):
         nu = max([len(t.nodes[v].u) for v in take]) if kind == "LIN" else 0
         nw = max([len(t.nodes[v].w) for v in take]) if kind == "LIN" else 0
         assert nu + nw <= MAX_TERMS, (nu, nw)
-        cost += {"MUL": 700, "CONJ": 100, "INV": 40000}.get(kind, lin_cost(nu, nw))
+        cost += {"MUL": 800, "CONJ": 100, "INV": 40000}.get(kind, lin_cost(nu, nw))
+        per_node = 2 if kind == "LIN" else 1        # a LIN node takes two lanes: one per coordinate of the Fq2 result
+        assert len(take) * per_node <= LANES
         for lane in range(LANES):
             w0 = KIND[kind] | (nu << 20) | (nw << 24)
-            if lane >= len(take):
+            if lane >= len(take) * per_node:
                 words += [w0, 0, 0, 0, 0, 0, 0, 0]
                 continue
-            v = take[lane]
+            v = take[lane // per_node]
             nd = t.nodes[v]
             w0 |= (1 << 4) | (slot[v] << 8)
             if kind == "LIN":
+                w0 |= (lane & 1) << 17
+                assert sum(abs(c) for _, c in nd.u) + 10 * sum(abs(c) for _, c in nd.w) <= LIN_BOUND
+
                 def enc(x, c):
                     assert 1 <= abs(c) <= MAX_COEF
                     return s_of(x) | (int(c < 0) << 9) | ((abs(c) - 1) << 10)
-                assert sum(abs(c) for _, c in nd.u) + 10 * sum(abs(c) for _, c in nd.w) <= LIN_BOUND
                 tt = [0] * 14
                 for k, (x, c) in enumerate(nd.u):
                     tt[k] = enc(x, c)
                 for k, (x, c) in enumerate(nd.w):
-                    tt[13 - k] = enc(x, c)
+                    tt[nu + k] = enc(x, c)
                 words += [w0] + [tt[2 * k] | (tt[2 * k + 1] << 16) for k in range(7)]
             elif kind == "MUL":
                 a1, a2, b1, b2 = (s_of(x) for x in nd.srcs)
@@ -481,7 +585,7 @@ def simulate(prog, inputs):
     for s, v in zip(prog["inputs"], inputs):
         S[s] = v
     for idx, s in prog["consts"].items():
-        S[s] = gp.CONSTS[idx]
+        S[s] = WP_CONSTS[idx]
     w = prog["words"]
     for step in range(prog["nsteps"]):
         writes = []
@@ -490,7 +594,7 @@ def simulate(prog, inputs):
             w0, w1, w2 = d8[0], d8[1], d8[2]
             if not (w0 >> 4) & 1:
                 continue
-            kind, dst, nu, nw = KINDS[w0 & 15], (w0 >> 8) & 511, (w0 >> 20) & 15, (w0 >> 24) & 15
+            kind, dst, nu, nw, half = KINDS[w0 & 15], (w0 >> 8) & 511, (w0 >> 20) & 15, (w0 >> 24) & 15, (w0 >> 17) & 1
             if kind == "MUL":
                 a1, a2, b1, b2 = w1 & 0xFFFF, w1 >> 16, w2 & 0xFFFF, w2 >> 16
                 a = ((S[a1][0] + S[a2][0]) % Q, (S[a1][1] + S[a2][1]) % Q)
@@ -498,23 +602,26 @@ def simulate(prog, inputs):
                 r = gp.f2_mul(a, b)
             elif kind == "LIN":
                 tt = [(x >> (16 * k)) & 0xFFFF for x in d8[1:] for k in range(2)]
-                u, ww = [0, 0], [0, 0]
-                for k in list(range(nu)) + [13 - j for j in range(nw)]:
-                    acc = u if k < nu else ww
-                    sg = (-1 if (tt[k] >> 9) & 1 else 1) * (((tt[k] >> 10) & 63) + 1)
+                acc = 0
+                for k in range(nu + nw):
+                    c = (-1 if (tt[k] >> 9) & 1 else 1) * (((tt[k] >> 10) & 63) + 1)
                     x = S[tt[k] & 511]
-                    acc[0] += sg * x[0]
-                    acc[1] += sg * x[1]
-                r = ((u[0] + 9 * ww[0] - ww[1]) % Q, (u[1] + 9 * ww[1] + ww[0]) % Q)
+                    if k < nu:
+                        acc += c * x[half]
+                    else:
+                        acc += 9 * c * x[half] + (c if half else -c) * x[1 - half]
+                writes.append((dst, half, acc % Q))
+                continue
             elif kind == "CONJ":
                 r = (S[w1][0], -S[w1][1] % Q)
             elif kind == "INV":
                 r = gp.f2_inv(S[w1]) if S[w1] != (0, 0) else (0, 0)
             else:
                 raise ValueError(kind)
-            writes.append((dst, r))
-        for dst, r in writes:
-            S[dst] = r
+            writes.append((dst, 0, r[0]))
+            writes.append((dst, 1, r[1]))
+        for dst, half, r in writes:
+            S[dst] = (r, S[dst][1]) if half == 0 else (S[dst][0], r)
     return [S[s] for s in prog["outs"]]
 
 
@@ -523,8 +630,8 @@ def simulate(prog, inputs):
 # ---------------------------------------------------------------------------------------------
 def compact(prog):
     """(step headers, node stream) of the dense descriptor array: per step one header word kind | nactive << 4 | nU << 20 |
-    nW << 24, per active lane the destination slot followed by its payload (MUL: 2 words, LIN: the nU + nW terms two per
-    word, CONJ / INV: 1 word).  wpprog::expand() (emitted below) rebuilds the dense array the kernel reads."""
+    nW << 24, per active lane (LIN: per pair of lanes) the destination slot followed by its payload (MUL: 2 words, LIN: the
+    nU + nW terms two per word, CONJ / INV: 1 word).  wpprog::expand() (emitted below) rebuilds the dense array the kernel reads."""
     w = prog["words"]
     hdr, stream = [], []
     for step in range(prog["nsteps"]):
@@ -538,14 +645,13 @@ def compact(prog):
                 continue
             assert lane == nact
             nact += 1
+            if KINDS[kind] == "LIN" and lane & 1:
+                continue                      # the second lane of a LIN node repeats the first
             stream.append((d[0] >> 8) & 511)
             if KINDS[kind] == "MUL":
                 stream += [d[1], d[2]]
             elif KINDS[kind] == "LIN":
-                tt = [(x >> (16 * k)) & 0xFFFF for x in d[1:] for k in range(2)]
-                seq = tt[:nu] + [tt[13 - k] for k in range(nw)]
-                seq += [0] * (len(seq) & 1)
-                stream += [seq[2 * k] | (seq[2 * k + 1] << 16) for k in range(len(seq) // 2)]
+                stream += d[1:1 + (nu + nw + 1) // 2]
             else:
                 stream.append(d[1])
         hdr.append(kind | (nact << 4) | (nu << 20) | (nw << 24))
@@ -562,19 +668,15 @@ static inline void expand(const Program& p, uint32_t* words) {
       for (int k = 0; k < 8; k++) d[k] = 0;
       d[0] = kind | (nu << 20) | (nw << 24);
       if (lane >= nact) continue;
+      if (kind == K_LIN && (lane & 1u)) {   // second lane of a LIN node: same descriptor, other coordinate
+        for (int k = 0; k < 8; k++) d[k] = d[k - 8];
+        d[0] |= 1u << 17;
+        continue;
+      }
       d[0] |= (1u << 4) | (*s++ << 8);
       if (kind == K_MUL) { d[1] = *s++; d[2] = *s++; }
-      else if (kind == K_LIN) {
-        uint16_t tt[14] = {0};
-        const uint32_t n = nu + nw;
-        for (uint32_t k = 0; k < n; k += 2) {
-          const uint32_t x = *s++;
-          const uint32_t t0 = x & 0xffffu, t1 = x >> 16;
-          if (k < nu) tt[k] = (uint16_t)t0; else tt[13 - (k - nu)] = (uint16_t)t0;
-          if (k + 1 < n) { if (k + 1 < nu) tt[k + 1] = (uint16_t)t1; else tt[13 - (k + 1 - nu)] = (uint16_t)t1; }
-        }
-        for (int k = 0; k < 7; k++) d[1 + k] = tt[2 * k] | ((uint32_t)tt[2 * k + 1] << 16);
-      } else d[1] = *s++;
+      else if (kind == K_LIN) { for (uint32_t k = 0; k < (nu + nw + 1) / 2; k++) d[1 + k] = *s++; }
+      else d[1] = *s++;
     }
   }
 }"""
@@ -589,22 +691,20 @@ def expand_py(prog, hdr, stream):
         for lane in range(LANES):
             d = [kind | (nu << 20) | (nw << 24)] + [0] * 7
             if lane < nact:
+                if KINDS[kind] == "LIN" and lane & 1:
+                    d = list(out[-8:])
+                    d[0] |= 1 << 17
+                    out += d
+                    continue
                 d[0] |= (1 << 4) | (stream[pos] << 8)
                 pos += 1
                 if KINDS[kind] == "MUL":
                     d[1], d[2] = stream[pos], stream[pos + 1]
                     pos += 2
                 elif KINDS[kind] == "LIN":
-                    tt = [0] * 14
-                    n = nu + nw
-                    for k in range(0, n, 2):
-                        x = stream[pos]
-                        pos += 1
-                        for j, t in ((k, x & 0xFFFF), (k + 1, x >> 16)):
-                            if j < n:
-                                tt[j if j < nu else 13 - (j - nu)] = t
-                    for k in range(7):
-                        d[1 + k] = tt[2 * k] | (tt[2 * k + 1] << 16)
+                    n = (nu + nw + 1) // 2
+                    d[1:1 + n] = stream[pos:pos + n]
+                    pos += n
                 else:
                     d[1] = stream[pos]
                     pos += 1
@@ -621,10 +721,10 @@ def main():
            "enum Kind : uint32_t { " + ", ".join("K_%s = %d" % (n, i) for i, n in enumerate(KINDS)) + " };",
            "struct Program { int nsteps, nslots, ninputs, nconsts, nouts; const uint16_t* inputs; const uint16_t* const_idx; const uint16_t* const_slot; "
            "const uint16_t* outs; const uint32_t* hdr; const uint32_t* stream; };"]
-    out.append("static const int NUM_CONSTS = %d;" % len(gp.CONSTS))
-    out.append("// Fq2 constants (Montgomery form): " + ", ".join(gp.CONST_NAMES))
-    out.append("static const uint32_t CONSTS[%d * 16] = {" % len(gp.CONSTS))
-    for c in gp.CONSTS:
+    out.append("static const int NUM_CONSTS = %d;" % len(WP_CONSTS))
+    out.append("// Fq2 constants (Montgomery form): " + ", ".join(WP_CONST_NAMES))
+    out.append("static const uint32_t CONSTS[%d * 16] = {" % len(WP_CONSTS))
+    for c in WP_CONSTS:
         out.append("    " + gp.limbs(c[0] * gp.MONT % Q) + ", " + gp.limbs(c[1] * gp.MONT % Q) + ",")
     out.append("};")
     names = []
