@@ -120,6 +120,7 @@ struct kb_ctx {
   uint16_t* d_wp_outs[2] = {nullptr, nullptr};
   uint32_t* d_wp_consts = nullptr;
   uint64_t wp_max_n = 0;
+  bool ntt_radix2 = false;           // KB_NTT_RADIX2=1: one radix-2 stage per launch even for small G1 transforms (measurement)
 
   // FK open-all cache: hat_s = DFT_2d(reversed SRS prefix) per d
   struct FkCache { uint64_t d = 0; uint32_t* d_hat_s = nullptr; };

@@ -180,6 +180,7 @@ void wp_init(kb_ctx* ctx) {
   // kernel, whose floor is a lone warp's 9.1 ms (4096 pairings: 6.0 ms here, 8192: 11.4)
   ctx->wp_max_n = 6144;
   if (const char* e = getenv("KB_PAIRING_WARP_MAX")) ctx->wp_max_n = strtoull(e, nullptr, 10);
+  if (const char* e = getenv("KB_NTT_RADIX2")) ctx->ntt_radix2 = atoi(e) != 0;
 }
 void wp_free(kb_ctx* ctx) {
   for (int which = 0; which < 2; which++) {

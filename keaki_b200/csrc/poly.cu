@@ -202,6 +202,82 @@ __global__ void __launch_bounds__(128) g1_butterfly4_kernel(uint32_t* __restrict
   if (ql.q == 0) { st_g1x(a + 32 * (size_t)i, r0); st_g1x(a + 32 * (size_t)j, r1); }
 }
 
+// R merged stages (s .. s+R-1) in ONE pass for the latency-bound sizes.  A stage of a small transform waits for one scalar
+// multiplication per butterfly, and the stages are dependent: 13 multiplications in sequence for 2^13 points.  The
+// transform is linear, so the 2^R outputs of a radix-2^R butterfly are signed sums of (twiddle product) x (input) terms
+// that can all be computed at once:
+//     y_f = a_0 + sum_{e = 1}^{2^R - 1} (-1)^popcount(e & f) w^E(e, f mod 2^h(e)) a_e,     h(e) = index of the top bit of e,
+//     E(e, v) = sum_{t : bit t of e set} (k + (v mod 2^t) 2^s) 2^(L - 1 - s - t)
+// (the path of input e through the R radix-2 stages picks up stage t's twiddle exactly when bit t of e is set, and by then
+// the low t bits of its position are those of the output f).  Input e needs 2^h(e) distinct products: 1 + 4 + 16 = 21
+// scalar multiplications per radix-8 butterfly instead of 12 - but one multiplication deep instead of three.
+__device__ __forceinline__ int r8_job(int e, int v) { return e == 1 ? 0 : e < 4 ? 1 + (e - 2) * 2 + v : 5 + (e - 4) * 4 + v; }
+template <int R> struct R8Jobs { static constexpr int N = R == 1 ? 1 : R == 2 ? 5 : 21; };
+
+// QUAD: four lanes share one multiplication (shorter dependent chain, four times the lanes); worth it only while the
+// lanes are free - a radix-8 pass over 2^13 points has 21.5 K multiplications, and with one THREAD each they still run at
+// lone-warp speed (a warp or two per scheduler) while the quad form is throughput-bound (measured 2.05 ms against 0.6)
+template <int R, bool QUAD>
+__global__ void __launch_bounds__(128) g1_radix_mul_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ tw_canon, int logn, int s,
+                                                           uint32_t* __restrict__ T) {
+  constexpr int NJ = R8Jobs<R>::N;
+  const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t qi = QUAD ? gt >> 2 : gt;
+  const QuadLane ql = quad_lane();
+  const uint32_t groups = 1u << (logn - R);
+  if (qi >= groups * NJ) return;   // whole quads leave together
+  const uint32_t group = qi / NJ, jidx = qi % NJ;
+  int e, v;
+  if (jidx == 0) { e = 1; v = 0; }
+  else if (jidx < 5) { e = 2 + (jidx - 1) / 2; v = (jidx - 1) & 1; }
+  else { e = 4 + (jidx - 5) / 4; v = (jidx - 5) & 3; }
+  const uint32_t k = group & ((1u << s) - 1), base = ((group >> s) << (s + R)) + k;
+  uint32_t E = 0;
+#pragma unroll
+  for (int t = 0; t < R; t++)
+    if ((e >> t) & 1) E += (k + ((uint32_t)(v & ((1 << t) - 1)) << s)) << (logn - 1 - s - t);
+  E &= (1u << logn) - 1;
+  G1 p = ld_g1x(a + 32 * (size_t)(base + ((uint32_t)e << s)));
+  const uint32_t idx = E & ((1u << (logn - 1)) - 1);
+  if (idx != 0 && !p.is_inf()) {
+    uint32_t kk[8];
+    const uint32_t* src = tw_canon + 8 * (size_t)idx;
+    for (int q = 0; q < 8; q++) kk[q] = src[q];
+    if (QUAD) p = g1_mul_glv4(p, kk, ql);
+    else p = g1_mul_glv(p, kk);
+  }
+  if (E >> (logn - 1)) p = neg(p);      // w^(n/2) = -1
+  if (!QUAD || ql.q == 0) st_g1x(T + 32 * (size_t)qi, p);
+}
+
+template <int R>
+__global__ void __launch_bounds__(128) g1_radix_sum_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ T, int logn, int s,
+                                                           uint32_t* __restrict__ out) {
+  constexpr int NJ = R8Jobs<R>::N;
+  const uint32_t qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const QuadLane ql = quad_lane();
+  if (qi >= (1u << logn)) return;
+  const uint32_t group = qi >> R, f = qi & ((1u << R) - 1);
+  const uint32_t k = group & ((1u << s) - 1), base = ((group >> s) << (s + R)) + k;
+  G1 acc = ld_g1x(a + 32 * (size_t)base);
+#pragma unroll 1
+  for (int e = 1; e < (1 << R); e++) {
+    const int h = e >= 4 ? 2 : e >= 2 ? 1 : 0;
+    G1 t = ld_g1x(T + 32 * ((size_t)group * NJ + r8_job(e, f & ((1 << h) - 1))));
+    if (__popc(e & f) & 1) t = neg(t);
+    acc = g1_add4(acc, t, ql);
+  }
+  if (ql.q == 0) st_g1x(out + 32 * (size_t)(base + (f << s)), acc);
+}
+
+template <int R>
+static void g1_radix_pass(kb_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t* T, const uint32_t* tw_canon, int logn, int s) {
+  const uint64_t jobs = (uint64_t)R8Jobs<R>::N << (logn - R);
+  if (jobs <= 4096) KB_LAUNCH(ctx, (g1_radix_mul_kernel<R, true>), cdiv(4 * jobs, 128), 128, 0, in, tw_canon, logn, s, T);
+  else KB_LAUNCH(ctx, (g1_radix_mul_kernel<R, false>), cdiv(jobs, 128), 128, 0, in, tw_canon, logn, s, T);
+  KB_LAUNCH(ctx, (g1_radix_sum_kernel<R>), cdiv(4ull << logn, 128), 128, 0, in, T, logn, s, out);
+}
+
 // in-place natural-order G1 transform on d_pts (XYZZ), unscaled
 static void g1_ntt_dev(kb_ctx* ctx, uint32_t* d_pts, int logn, bool inverse) {
   if (logn == 0) return;
@@ -209,6 +285,22 @@ static void g1_ntt_dev(kb_ctx* ctx, uint32_t* d_pts, int logn, bool inverse) {
   Twiddles tw(ctx, logn, inverse, true);
   DevBuf<uint32_t> tmp(ctx, 32 * n);
   KB_LAUNCH(ctx, g1_bitrev_kernel, cdiv(n, 256), 256, 0, d_pts, tmp.p, logn);
+  if (n <= (1ull << 14) && !ctx->ntt_radix2) {   // latency-bound sizes: merged stages, ping-pong between tmp and d_pts
+    DevBuf<uint32_t> T(ctx, 32 * ((uint64_t)21 << (logn >= 3 ? logn - 3 : 0)));
+    uint32_t* cur = tmp.p;
+    uint32_t* nxt = d_pts;
+    int s = 0;
+    while (s < logn) {
+      const int r = logn - s >= 3 ? 3 : logn - s;
+      if (r == 3) g1_radix_pass<3>(ctx, cur, nxt, T.p, tw.canon.p, logn, s);
+      else if (r == 2) g1_radix_pass<2>(ctx, cur, nxt, T.p, tw.canon.p, logn, s);
+      else g1_radix_pass<1>(ctx, cur, nxt, T.p, tw.canon.p, logn, s);
+      s += r;
+      uint32_t* x = cur; cur = nxt; nxt = x;
+    }
+    if (cur != d_pts) KB_CUDA(cudaMemcpyAsync(d_pts, cur, 128 * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    return;
+  }
   const bool quads = n <= (1ull << 14);   // latency-bound sizes
   for (int s = 0; s < logn; s++) {
     if (quads) KB_LAUNCH(ctx, g1_butterfly4_kernel, cdiv(2 * n, 128), 128, 0, tmp.p, tw.canon.p, logn, s);

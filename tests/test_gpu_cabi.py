@@ -198,7 +198,7 @@ def test_open_batch_and_verify(ctx, srs):
     assert inf[0] == 1
 
 
-@pytest.mark.parametrize("d", [1, 2, 8, 64])
+@pytest.mark.parametrize("d", [1, 2, 4, 8, 16, 32, 64, 256])
 def test_open_all_fk(ctx, srs, d):
     p = [rng.randrange(bn.R) for _ in range(d)]
     proofs, inf = ctx.open_all_fk(L.fr_vec(p).reshape(d, 8))
