@@ -116,10 +116,12 @@ struct kb_ctx {
   int pairing_impl = 1;              // 0 = pairing VM (two lanes + interpreter), 1 = compiled single-thread kernel; KB_PAIRING_IMPL=vm|st
   // warp-cooperative pairing (pairing_warp.cu): dense step descriptors of the two schedules (pairing, GT window bases),
   // their output slots, the Fq2 constants; batches of at most wp_max_n pairings use it (KB_PAIRING_WARP_MAX, 0 = never)
-  uint32_t* d_wp_words[2] = {nullptr, nullptr};
-  uint16_t* d_wp_outs[2] = {nullptr, nullptr};
+  uint32_t* d_wp_words[3] = {nullptr, nullptr, nullptr};   // schedules: pairing, GT window bases, GT product of 48
+  uint16_t* d_wp_outs[3] = {nullptr, nullptr, nullptr};
+  uint16_t* d_wp_ins = nullptr;      // input slots of the GT product schedule
   uint32_t* d_wp_consts = nullptr;
   uint64_t wp_max_n = 0;
+  uint64_t wp_enc_max_n = 0;         // kb_encrypt_batch: batches of at most this many messages take one warp per message (KB_ENCRYPT_WARP_MAX)
   bool ntt_radix2 = false;           // KB_NTT_RADIX2=1: one radix-2 stage per launch even for small G1 transforms (measurement)
 
   // FK open-all cache: hat_s = DFT_2d(reversed SRS prefix) per d
@@ -205,6 +207,25 @@ inline void timers_collect(kb_ctx* c) {
     if (c->last_ms[i] == -2.f) { float ms = -1.f; if (cudaEventElapsedTime(&ms, c->ev[2 * i], c->ev[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); ms = -1.f; } c->last_ms[i] = ms; }
 }
 
+// ---- fixed-base window tables of the witness encryption (we.cu builds them, we.cu and pairing_warp.cu read them)
+static constexpr int WE_WIN = 32;          // 8-bit windows over 256 bits
+static constexpr int WE_ENT = 255;         // non-zero digits
+static constexpr size_t G2_TAB_LIMBS = (size_t)WE_WIN * WE_ENT * 32;
+static constexpr size_t GT_TAB_LIMBS = (size_t)WE_WIN * WE_ENT * 96;
+// Bases that are fixed for the life of an SRS (G2, tau_2, gT = e(G1, G2)) get 16-bit windows: 16 x 65535 entries
+// (128 MiB per G2 table, 384 MiB for gT) halve the group operations per message; HBM capacity is what B200 has to
+// spare.  A = e(com, G2) changes per commitment: it starts with 8-bit windows (32 + 8160 Fq12 products to build) and
+// is upgraded to 16-bit windows (one more Fq12 product per entry, ~1 M) once the commitment has served 2^16
+// messages - the point where the 16 products saved per message would have paid for the build (laconic OT encrypts
+// 2 n messages under one commitment, tests/laconic_ot.rs:89-109).
+static constexpr int WE_WIN16 = 16;
+static constexpr int WE_ENT16 = 65535;
+static constexpr size_t G2_TAB16_LIMBS = (size_t)WE_WIN16 * WE_ENT16 * 32;
+static constexpr size_t GT_TAB16_LIMBS = (size_t)WE_WIN16 * WE_ENT16 * 96;
+
+__device__ __forceinline__ uint32_t byte_of(const uint32_t* k, int w) { return (k[w >> 2] >> ((w & 3) * 8)) & 255u; }
+__device__ __forceinline__ uint32_t half_of(const uint32_t* k, int w) { return (k[w >> 1] >> ((w & 1) * 16)) & 65535u; }
+
 inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
 // device-side loaders shared by the kernels
@@ -253,6 +274,10 @@ void wp_free(kb_ctx* ctx);
 void wp_pairing_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf, uint64_t n,
                        int mode, uint32_t* d_gt, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out);
 void wp_gt_bases_launch(kb_ctx* ctx, const uint32_t* d_a, uint32_t* d_bases);   // bases[w] = a^(2^(8w)), w < 32
+void wp_encrypt_small_launch(kb_ctx* ctx, const uint32_t* com_tab_a, const uint32_t* com_tab_a1, int com_wide, const uint32_t* gt_tab16,
+                             const uint32_t* tau2_tab16, const uint32_t* g2_tab16, const uint32_t* d_points, const uint32_t* d_values,
+                             const uint32_t* d_r, const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n, uint32_t* d_ct, uint8_t* d_ct_inf,
+                             uint8_t* d_msg_ct);
 void pairing_batch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
                    uint64_t n, uint8_t* d_gt_bytes);
 void decrypt_batch(kb_ctx* ctx, const uint32_t* d_proofs, const uint8_t* d_pinf, const uint32_t* d_ct, const uint8_t* d_cinf,

@@ -56,6 +56,7 @@ struct WpArgs {
   const uint4* words;        // dense descriptors: 2 uint4 per lane, 64 per step
   const uint32_t* consts;    // wpprog::CONSTS on the device
   const uint16_t* outs;      // output slots (device)
+  const uint16_t* ins;       // input slots of GT_PROD (device)
   int nsteps, nslots, nconsts, nouts;
   uint16_t inputs[8];
   uint16_t const_idx[24], const_slot[24];
@@ -148,17 +149,111 @@ __global__ void __launch_bounds__(64) gt_xof_xor_kernel(const uint32_t* __restri
   b3_gt_xof_xor(w, msg_ct + lo, out + lo, hi - lo);
 }
 
+// Small-batch `encrypt` (src/kem.rs:13-50 + the XOR of src/enc.rs:19-41): ONE WARP per message.  The thread-per-message
+// kernels of we.cu multiply 32-48 table entries in sequence (1.9 ms however few messages there are, plus 0.65 ms for the 32
+// dependent G2 additions); here the entries are gathered into the slot file and multiplied as a tree by the GT_PROD
+// schedule (47 Fq12 products, 89 steps), and the 32 G2 table entries - one per lane - are summed by a shuffle tree.
+// Same table lookups, same group elements: identical ciphertexts.
+__device__ __forceinline__ G2 g2_shfl_down(const G2& p, int delta) {
+  G2 r;
+  const Fq2* src[4] = {&p.x, &p.y, &p.zz, &p.zzz};
+  Fq2* dst[4] = {&r.x, &r.y, &r.zz, &r.zzz};
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      dst[c]->c0.v[i] = __shfl_down_sync(0xffffffffu, src[c]->c0.v[i], delta);
+      dst[c]->c1.v[i] = __shfl_down_sync(0xffffffffu, src[c]->c1.v[i], delta);
+    }
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(32) encrypt_small_kernel(WpArgs a, const uint32_t* __restrict__ com_tab_a, const uint32_t* __restrict__ com_tab_a1,
+                                                           int com_wide, const uint32_t* __restrict__ gt_tab, const uint32_t* __restrict__ tau2_tab,
+                                                           const uint32_t* __restrict__ g2_tab, const uint32_t* __restrict__ points,
+                                                           const uint32_t* __restrict__ values, const uint32_t* __restrict__ rs,
+                                                           const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off, uint64_t n,
+                                                           uint32_t* __restrict__ ct, uint8_t* __restrict__ ct_inf, uint8_t* __restrict__ msg_ct) {
+  const uint32_t lane = threadIdx.x;
+  WpDevMem m{wp_smem, (uint32_t)a.nslots};
+  wp_prologue(m, a, lane);
+  for (uint64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const Fr r = fp_load<FrParams>(rs + 8 * i), v = fp_load<FrParams>(values + 8 * i), al = fp_load<FrParams>(points + 8 * i);
+    const Fr kr = fp_from_mont<FrParams>(r);
+    const bool v_one = v == Fr::one(), v_bit = v_one || v.is_zero();
+    const uint32_t* com_tab = v_one ? com_tab_a1 : com_tab_a;
+    const Fr ks = v_bit ? Fr::zero() : fp_from_mont<FrParams>(-(v * r));
+    // ---- GT side: operands 0..31 = the windows of A (or A'), 32..47 = those of gT; digit 0 or an unused operand = 1
+    for (int p = lane; p < 48 * 6; p += 32) {
+      const int el = p / 6, comp = p % 6;
+      const uint32_t* src = nullptr;
+      if (el < 32) {
+        if (com_wide) { if (el < WE_WIN16) { const uint32_t d = half_of(kr.v, el); if (d) src = com_tab + 96 * ((size_t)el * WE_ENT16 + d - 1); } }
+        else { const uint32_t d = byte_of(kr.v, el); if (d) src = com_tab + 96 * ((size_t)el * WE_ENT + d - 1); }
+      } else {
+        const uint32_t d = half_of(ks.v, el - 32);
+        if (d) src = gt_tab + 96 * ((size_t)(el - 32) * WE_ENT16 + d - 1);
+      }
+      Fq2 x = comp == 0 ? Fq2::one() : Fq2::zero();
+      if (src) x = st::ld_const2(src + 16 * comp);
+      m.st(a.ins[p], x);
+    }
+    __syncwarp();
+    wp_run(m, a, lane);
+    if (lane < 6) {   // canonical words, staged in the slot file for the hashing lane
+      Fq2 x = m.ld(a.outs[lane]);
+      Fq unit = Fq::zero(); unit.v[0] = 1;
+      x.c0 = st::f1mul(x.c0, unit); x.c1 = st::f1mul(x.c1, unit);
+      m.st(a.outs[lane], x);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t w[96];
+#pragma unroll
+      for (int s = 0; s < 6; s++) {
+        const Fq2 x = m.ld(a.outs[s]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { w[16 * s + k] = x.c0.v[k]; w[16 * s + 8 + k] = x.c1.v[k]; }
+      }
+      const uint64_t lo = off[i], hi = off[i + 1];
+      b3_gt_xof_xor(w, msgs + lo, msg_ct + lo, hi - lo);
+    }
+    __syncwarp();
+    // ---- G2 side: ct = r tau_2 - (r alpha) G2; lane l holds window l >> 1 of tau_2 (even lanes) or of -G2 (odd lanes)
+    {
+      const Fr ka = fp_from_mont<FrParams>(r * al);
+      const uint32_t w = lane >> 1;
+      const uint32_t d = half_of((lane & 1) ? ka.v : kr.v, w);
+      G2 acc = G2::infinity();
+      if (d) {
+        G2Affine t = ld_g2(((lane & 1) ? g2_tab : tau2_tab) + 32 * ((size_t)w * WE_ENT16 + d - 1));
+        if (lane & 1) t.y = -t.y;
+        acc = to_xyzz(t);
+      }
+#pragma unroll 1
+      for (int delta = 16; delta >= 1; delta >>= 1) acc = ec_add(acc, g2_shfl_down(acc, delta));
+      if (lane == 0) {
+        st_g2(ct + 32 * i, to_affine(acc));
+        ct_inf[i] = acc.is_inf() ? 1 : 0;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static WpArgs wp_args(kb_ctx* ctx, int which) {
-  const wpprog::Program& p = which == 0 ? wpprog::PAIRING : wpprog::GT_BASES;
+  const wpprog::Program& p = which == 0 ? wpprog::PAIRING : which == 1 ? wpprog::GT_BASES : wpprog::GT_PROD;
   WpArgs a{};
   a.words = reinterpret_cast<const uint4*>(ctx->d_wp_words[which]);
   a.consts = ctx->d_wp_consts;
   a.outs = ctx->d_wp_outs[which];
   a.nsteps = p.nsteps; a.nslots = p.nslots; a.nconsts = p.nconsts; a.nouts = p.nouts;
-  for (int i = 0; i < p.ninputs; i++) a.inputs[i] = p.inputs[i];
+  for (int i = 0; i < p.ninputs && i < 8; i++) a.inputs[i] = p.inputs[i];   // GT_PROD's 288 input slots are read from d_wp_ins
+  a.ins = ctx->d_wp_ins;
   for (int i = 0; i < p.nconsts; i++) { a.const_idx[i] = p.const_idx[i]; a.const_slot[i] = p.const_slot[i]; }
   return a;
 }
@@ -167,8 +262,8 @@ void wp_init(kb_ctx* ctx) {
   static_assert(wpprog::NUM_CONSTS <= 24, "constant table of WpArgs");
   KB_CUDA(cudaMalloc((void**)&ctx->d_wp_consts, sizeof(wpprog::CONSTS)));
   KB_CUDA(cudaMemcpyAsync(ctx->d_wp_consts, wpprog::CONSTS, sizeof(wpprog::CONSTS), cudaMemcpyHostToDevice, ctx->stream));
-  for (int which = 0; which < 2; which++) {
-    const wpprog::Program& p = which == 0 ? wpprog::PAIRING : wpprog::GT_BASES;
+  for (int which = 0; which < 3; which++) {
+    const wpprog::Program& p = which == 0 ? wpprog::PAIRING : which == 1 ? wpprog::GT_BASES : wpprog::GT_PROD;
     std::vector<uint32_t> words((size_t)p.nsteps * 32 * 8);
     wpprog::expand(p, words.data());
     KB_CUDA(cudaMalloc((void**)&ctx->d_wp_words[which], words.size() * 4));
@@ -176,14 +271,19 @@ void wp_init(kb_ctx* ctx) {
     KB_CUDA(cudaMalloc((void**)&ctx->d_wp_outs[which], p.nouts * 2));
     KB_CUDA(cudaMemcpy(ctx->d_wp_outs[which], p.outs, p.nouts * 2, cudaMemcpyHostToDevice));
   }
+  KB_CUDA(cudaMalloc((void**)&ctx->d_wp_ins, wpprog::GT_PROD.ninputs * 2));
+  KB_CUDA(cudaMemcpy(ctx->d_wp_ins, wpprog::GT_PROD.inputs, wpprog::GT_PROD.ninputs * 2, cudaMemcpyHostToDevice));
   // Batches up to this many pairings take the warp-cooperative kernel: measured crossover with the one-thread-per-pairing
   // kernel, whose floor is a lone warp's 9.1 ms (4096 pairings: 6.0 ms here, 8192: 11.4)
   ctx->wp_max_n = 6144;
   if (const char* e = getenv("KB_PAIRING_WARP_MAX")) ctx->wp_max_n = strtoull(e, nullptr, 10);
+  ctx->wp_enc_max_n = 2048;   // one warp per message below this (measured crossover with the thread-per-message kernels: DESIGN.md 4.2)
+  if (const char* e = getenv("KB_ENCRYPT_WARP_MAX")) ctx->wp_enc_max_n = strtoull(e, nullptr, 10);
   if (const char* e = getenv("KB_NTT_RADIX2")) ctx->ntt_radix2 = atoi(e) != 0;
 }
 void wp_free(kb_ctx* ctx) {
-  for (int which = 0; which < 2; which++) {
+  cudaFree(ctx->d_wp_ins); ctx->d_wp_ins = nullptr;
+  for (int which = 0; which < 3; which++) {
     cudaFree(ctx->d_wp_words[which]); ctx->d_wp_words[which] = nullptr;
     cudaFree(ctx->d_wp_outs[which]); ctx->d_wp_outs[which] = nullptr;
   }
@@ -230,6 +330,25 @@ void wp_gt_bases_launch(kb_ctx* ctx, const uint32_t* d_a, uint32_t* d_bases) {
     if (ctx->device < 64) prepared[ctx->device] = true;
   }
   KB_LAUNCH(ctx, gt_bases_warp_kernel, 1, 32, smem, a, d_a, d_bases);
+}
+
+void wp_encrypt_small_launch(kb_ctx* ctx, const uint32_t* com_tab_a, const uint32_t* com_tab_a1, int com_wide, const uint32_t* gt_tab16,
+                             const uint32_t* tau2_tab16, const uint32_t* g2_tab16, const uint32_t* d_points, const uint32_t* d_values,
+                             const uint32_t* d_r, const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n, uint32_t* d_ct, uint8_t* d_ct_inf,
+                             uint8_t* d_msg_ct) {
+  const WpArgs a = wp_args(ctx, 2);
+  const int smem = a.nslots * 64;
+  static bool prepared[64] = {};
+  if (ctx->device >= 64 || !prepared[ctx->device]) {
+    KB_CUDA(cudaFuncSetAttribute(encrypt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (ctx->device < 64) prepared[ctx->device] = true;
+  }
+  int per_sm = 0;
+  KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encrypt_small_kernel, 32, smem));
+  uint64_t blocks = (uint64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
+  if (blocks > n) blocks = n;
+  KB_LAUNCH(ctx, encrypt_small_kernel, (unsigned)blocks, 32, smem, a, com_tab_a, com_tab_a1, com_wide, gt_tab16, tau2_tab16, g2_tab16, d_points, d_values,
+            d_r, d_msgs, d_off, n, d_ct, d_ct_inf, d_msg_ct);
 }
 
 }  // namespace kb

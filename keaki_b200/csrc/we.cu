@@ -27,21 +27,6 @@ void we_upload_consts() {
   KB_CUDA(cudaMemcpyToSymbol(c_pc, &pc, sizeof(pc)));
 }
 
-static constexpr int WE_WIN = 32;          // 8-bit windows over 256 bits
-static constexpr int WE_ENT = 255;         // non-zero digits
-static constexpr size_t G2_TAB_LIMBS = (size_t)WE_WIN * WE_ENT * 32;
-static constexpr size_t GT_TAB_LIMBS = (size_t)WE_WIN * WE_ENT * 96;
-// Bases that are fixed for the life of an SRS (G2, tau_2, gT = e(G1, G2)) get 16-bit windows: 16 x 65535 entries
-// (128 MiB per G2 table, 384 MiB for gT) halve the group operations per message; HBM capacity is what B200 has to
-// spare.  A = e(com, G2) changes per commitment: it starts with 8-bit windows (32 + 8160 Fq12 products to build) and
-// is upgraded to 16-bit windows (one more Fq12 product per entry, ~1 M) once the commitment has served 2^15
-// messages - the point where the 16 products saved per message have paid for the build (laconic OT encrypts
-// 2 n messages under one commitment, tests/laconic_ot.rs:89-109).
-static constexpr int WE_WIN16 = 16;
-static constexpr int WE_ENT16 = 65535;
-static constexpr size_t G2_TAB16_LIMBS = (size_t)WE_WIN16 * WE_ENT16 * 32;
-static constexpr size_t GT_TAB16_LIMBS = (size_t)WE_WIN16 * WE_ENT16 * 96;
-
 __device__ __forceinline__ G1Affine load_g1_flag(const uint32_t* xy, const uint8_t* inf, uint64_t i) {
   if (inf && inf[i]) return G1Affine::infinity();
   return ld_g1(xy + 16 * i);
@@ -202,8 +187,6 @@ void we_free(kb_ctx* ctx) {
 // ------------------------------------------------------------------------------------------
 // encrypt
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t byte_of(const uint32_t* k, int w) { return (k[w >> 2] >> ((w & 3) * 8)) & 255u; }
-__device__ __forceinline__ uint32_t half_of(const uint32_t* k, int w) { return (k[w >> 1] >> ((w & 1) * 16)) & 65535u; }
 
 // Two kernels per batch: the GT side (two fixed-base exponentiations, hash, XOR) keeps an Fq12 accumulator and a table
 // entry live (255 registers); the G2 side (two fixed-base multiplications, one affine normalisation) needs a third of
@@ -307,6 +290,13 @@ void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const
   }
   ctx->com_msgs += n;
   const bool wide = ctx->com_tab16_valid;
+  if (n <= ctx->wp_enc_max_n) {   // small batches: one warp per message (pairing_warp.cu), a thread needs 2.6 ms however few there are
+    timer_start(ctx, KB_T_ENCRYPT);
+    wp_encrypt_small_launch(ctx, wide ? ctx->d_com_tab16 : ctx->d_com_tab, wide ? ctx->d_com1_tab16 : ctx->d_com1_tab, wide ? 1 : 0, ctx->d_gt_tab16,
+                            ctx->d_tau2_tab16, ctx->d_g2_tab16, d_points, d_values, d_r, d_msgs, d_off, n, d_ct, d_ct_inf, d_msg_ct);
+    timer_stop(ctx, KB_T_ENCRYPT);
+    return;
+  }
   timer_start(ctx, KB_T_ENCRYPT);
   KB_LAUNCH(ctx, encrypt_kernel, cdiv(n, 128), 128, 0, wide ? ctx->d_com_tab16 : ctx->d_com_tab, wide ? ctx->d_com1_tab16 : ctx->d_com1_tab,
             ctx->d_gt_tab16, d_values, d_r, d_msgs, d_off, n, wide ? 1 : 0, d_msg_ct);

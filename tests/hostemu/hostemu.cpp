@@ -290,10 +290,11 @@ struct WpMem {
 
 extern "C" {
 
-// prog 0: pairing (inputs P, Qx, Qy, (xP, 0), (yP, 0)), 1: window bases of a GT table (input: a cyclotomic Fq12, tower order).
+// prog 0: pairing (inputs P, Qx, Qy, (xP, 0), (yP, 0)), 1: window bases of a GT table (input: a cyclotomic Fq12, tower order),
+// 2: product of 48 Fq12 values (tower order each).
 // Inputs / outputs as 16 Montgomery limbs per Fq2.
 int he_wp_run(int prog, const uint32_t* inputs, uint32_t* outs) {
-  const wpprog::Program& p = prog == 0 ? wpprog::PAIRING : wpprog::GT_BASES;
+  const wpprog::Program& p = prog == 0 ? wpprog::PAIRING : prog == 1 ? wpprog::GT_BASES : wpprog::GT_PROD;
   std::vector<Fq2> slots(p.nslots, Fq2::zero());
   for (int i = 0; i < p.ninputs; i++) slots[p.inputs[i]] = ldq2(inputs + 16 * i);
   for (int i = 0; i < p.nconsts; i++) slots[p.const_slot[i]] = ldq2(wpprog::CONSTS + 16 * p.const_idx[i]);

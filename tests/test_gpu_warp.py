@@ -29,6 +29,7 @@ def rand_fr_limbs(n):
 def ctx():
     from keaki_b200 import _ffi
     os.environ.pop("KB_PAIRING_WARP_MAX", None)
+    os.environ.pop("KB_ENCRYPT_WARP_MAX", None)
     c = _ffi.Context(0)
     yield c
     c.close()
@@ -39,10 +40,12 @@ def ctx_thread():
     """a context that never takes the warp-cooperative kernel"""
     from keaki_b200 import _ffi
     os.environ["KB_PAIRING_WARP_MAX"] = "0"
+    os.environ["KB_ENCRYPT_WARP_MAX"] = "0"
     try:
         c = _ffi.Context(0)
     finally:
         os.environ.pop("KB_PAIRING_WARP_MAX", None)
+        os.environ.pop("KB_ENCRYPT_WARP_MAX", None)
     yield c
     c.close()
 
@@ -106,3 +109,36 @@ def test_fresh_commitment_tables_both_paths(ctx, ctx_thread):
     b = ctx_thread.encrypt_batch(L.g1_m(com), 0, pts, vals, rs, msgs, off)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("n", [1, 33, 700])
+def test_small_encrypt_batches_warp_per_message(ctx, ctx_thread, n):
+    """kb_encrypt_batch below the small-batch threshold (one warp per message: GT product tree + G2 shuffle tree) against the
+    thread-per-message kernels and the C oracle: values 0, 1 and general, zero scalars, ragged message lengths"""
+    from oracle import coracle as co
+    for c in (ctx, ctx_thread):
+        c.srs_generate(L.fr_m(TAU), 64, download=False)
+    tau_g2 = L.g2_m(bn.g2_mul(bn.G2_GEN, TAU))
+    com = bn.g1_mul(bn.G1_GEN, rng.randrange(1, bn.R))
+    pts, vals, rs = rand_fr_limbs(n), rand_fr_limbs(n), rand_fr_limbs(n)
+    one = L.fr_m(1)
+    for i in range(n):
+        if i % 3 == 0:
+            vals[i] = 0
+        elif i % 3 == 1:
+            vals[i] = one
+    if n > 4:
+        rs[2] = 0          # r = 0: secret = 1, ct = infinity
+        pts[4] = 0         # alpha = 0
+    lens = nprng.integers(0, 90, size=n).astype(np.uint64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    msgs = nprng.integers(0, 256, size=max(int(off[-1]), 1), dtype=np.uint8)
+    a = ctx.encrypt_batch(L.g1_m(com), 0, pts, vals, rs, msgs, off)
+    b = ctx_thread.encrypt_batch(L.g1_m(com), 0, pts, vals, rs, msgs, off)
+    w = co.encrypt_batch(L.g1_m(com), 0, tau_g2, pts, vals, rs, msgs, off, threads=co.max_threads())
+    total = int(off[-1])
+    for x, y, z in zip(a, b, w):
+        x, y, z = (np.asarray(t).reshape(-1) for t in (x, y, z))
+        k = total if x.dtype == np.uint8 and x.size >= total and x.size != n else x.size
+        assert np.array_equal(x[:k], y[:k])
+        assert np.array_equal(x[:k], z[:k])

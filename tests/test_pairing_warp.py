@@ -86,6 +86,28 @@ def test_host_interpreter_runs_shipped_window_bases():
             x = bn.f12_sqr(x)
 
 
+def test_gt_product_schedule():
+    """GT_PROD: the product tree of 48 Fq12 operands behind the small-batch encrypt kernel (ones included, as for zero digits)"""
+    prog = gw.build("gt_prod")
+    assert prog["nslots"] <= gw.MAX_SLOTS and len(prog["inputs"]) == 48 * 6
+    one = ((((1, 0), (0, 0), (0, 0)), ((0, 0), (0, 0), (0, 0))))
+    xs = []
+    for k in range(48):
+        if k % 5 == 3:
+            xs.append(one)
+        else:
+            xs.append(tuple(tuple((rng.randrange(bn.Q), rng.randrange(bn.Q)) for _ in range(3)) for _ in range(2)))
+    want = xs[0]
+    for x in xs[1:]:
+        want = bn.f12_mul(want, x)
+    flat_in = [c for x in xs for c in _flat(x)]
+    assert gw.simulate(prog, flat_in) == _flat(want)
+    inp = HE.u32([w for v in flat_in for w in _mont2(v)])
+    out = np.zeros(6 * 16, dtype=np.uint32)
+    he.he_wp_run(2, P(inp), P(out))
+    assert [_from_mont2(list(out[16 * i:16 * i + 16])) for i in range(6)] == _flat(want)
+
+
 def test_reduce9_extremes():
     q = bn.Q
     vals = [0, 1, -1, q - 1, q, q + 1, -q, 127 * q, 128 * q - 1, -128 * q + 1, -127 * q - 1, 64 * q + (q >> 1)]

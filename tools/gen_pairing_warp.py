@@ -41,13 +41,14 @@ MAX_SLOTS = 440        # 28 KB of shared memory per warp
 MAX_TERMS = 14         # terms c * x one LIN descriptor holds
 MAX_COEF = 32
 LIN_BOUND = 120        # |integer value of a LIN| < LIN_BOUND * q
+GT_PROD_N = 48         # operands of the GT product schedule (32 window entries of A or A', 16 of gT; unused ones = 1)
 
 
 class Node:
-    __slots__ = ("kind", "srcs", "u", "w")
+    __slots__ = ("kind", "srcs", "u", "w", "phase")
 
     def __init__(self, kind, srcs=(), u=(), w=()):
-        self.kind, self.srcs, self.u, self.w = kind, list(srcs), list(u), list(w)
+        self.kind, self.srcs, self.u, self.w, self.phase = kind, list(srcs), list(u), list(w), 0
 
     def deps(self):
         return [s for s in self.srcs if s >= 0] + [v for v, _ in self.u] + [v for v, _ in self.w]
@@ -61,6 +62,7 @@ class WTrace:
         self.memo = {}
         self.outputs = []
         self.split = {}
+        self.phase = 0           # nodes of a later phase are scheduled after all nodes of the earlier ones (bounds live values)
 
     def new_input(self):
         self.nodes.append(None)
@@ -70,6 +72,7 @@ class WTrace:
     def emit(self, node, key):
         if key is not None and key in self.memo:
             return self.memo[key]
+        node.phase = self.phase
         self.nodes.append(node)
         vid = len(self.nodes) - 1
         if key is not None:
@@ -364,6 +367,28 @@ def trace(what):
             f = gp.final_exp(t, f)
             c0, c1 = gp.halves(f)
             outs = list(c0 + c1)
+        elif what == "gt_prod":
+            # product of GT_PROD_N Fq12 values (tower order each): chunks of 8 reduced one after the other (phases), so that
+            # at most one chunk's 96 level-1 products are alive next to the inputs
+            elems = []
+            for _ in range(GT_PROD_N):
+                tower = [EV.of(t, t.new_input()) for _ in range(6)]
+                elems.append([tower[0], tower[3], tower[1], tower[4], tower[2], tower[5]])
+
+            def tree(xs):
+                while len(xs) > 1:
+                    nxt = [[c.force() for c in gp.f12_mul(xs[i], xs[i + 1])] for i in range(0, len(xs) - 1, 2)]
+                    if len(xs) & 1:
+                        nxt.append(xs[-1])
+                    xs = nxt
+                return xs[0]
+            partial = []
+            for c in range(0, GT_PROD_N, 8):
+                t.phase = c // 8
+                partial.append(tree(elems[c:c + 8]))
+            t.phase = GT_PROD_N // 8
+            c0, c1 = gp.halves(tree(partial))
+            outs = list(c0 + c1)
         else:
             ids = [t.new_input() for _ in range(6)]
             tower = [EV.of(t, i) for i in ids]
@@ -439,7 +464,7 @@ def schedule(t):
     by_level = {}
     for v in live:
         if t.nodes[v] is not None:
-            by_level.setdefault(level[v], []).append(v)
+            by_level.setdefault((t.nodes[v].phase, level[v]), []).append(v)
     steps = []
     for lv in sorted(by_level):
         nodes = by_level[lv]
@@ -728,7 +753,7 @@ def main():
         out.append("    " + gp.limbs(c[0] * gp.MONT % Q) + ", " + gp.limbs(c[1] * gp.MONT % Q) + ",")
     out.append("};")
     names = []
-    for what in ("pairing", "gt_bases"):
+    for what in ("pairing", "gt_bases", "gt_prod"):
         p = build(what)
         hdr, stream = compact(p)
         assert expand_py(p, hdr, stream) == p["words"]
