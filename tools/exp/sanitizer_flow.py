@@ -1,7 +1,8 @@
 """Small pass over every entry point for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): MSM at both window
 widths (two-digit reduction, quad-cooperative tail) incl. the over-full-bucket path (all-equal scalars), SRS validation,
-open-all, encrypt (fresh commitment: the per-commitment pairing and tables), decrypt on the compiled pairing kernel and on
-the pairing VM, verify, wire format."""
+open-all (radix-8 passes), encrypt (fresh commitment: the per-commitment pairing and window bases on the warp-cooperative
+interpreter, the one-warp-per-message kernel), decrypt on the warp-cooperative kernel, on the compiled thread kernel and on
+the pairing VM, the thread-per-message encrypt kernels, verify, wire format."""
 import sys
 sys.path.insert(0, ".")
 import numpy as np
@@ -34,6 +35,17 @@ ct, cti, mc = ctx.encrypt_batch(com, ci, pts, vals, rnd(n), msgs, off)
 out = ctx.decrypt_batch(proofs, pinf, ct, cti, mc, off)
 assert bytes(out[: n * 32]) != b"" 
 import os
+os.environ["KB_PAIRING_WARP_MAX"] = "0"
+os.environ["KB_ENCRYPT_WARP_MAX"] = "0"
+th_ctx = _ffi.Context(0)          # the thread-per-pairing / thread-per-message kernels on the same inputs
+th_ctx.srs_generate(fr_to_limbs(tau), 1 << 14, download=False)
+rs_same = rnd(n)
+a1 = ctx.encrypt_batch(com, ci, pts, vals, rs_same, msgs, off)
+a2 = th_ctx.encrypt_batch(com, ci, pts, vals, rs_same, msgs, off)
+assert all(np.array_equal(x, y) for x, y in zip(a1, a2))
+assert np.array_equal(out, th_ctx.decrypt_batch(proofs, pinf, ct, cti, mc, off))
+th_ctx.close()
+os.environ.pop("KB_PAIRING_WARP_MAX"); os.environ.pop("KB_ENCRYPT_WARP_MAX")
 os.environ["KB_PAIRING_IMPL"] = "vm"
 vm_ctx = _ffi.Context(0)
 out_vm = vm_ctx.decrypt_batch(proofs, pinf, ct, cti, mc, off)
