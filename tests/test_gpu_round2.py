@@ -306,3 +306,43 @@ def test_msm_structured_scalars_do_not_serialise(ctx):
         acc = (acc * TAU + b) % bn.R
     assert g1_out(xy, inf) == bn.g1_mul(bn.G1_GEN, acc)
     assert ms < 12 * t_uniform + 5.0, f"0/1 scalars: {ms:.1f} ms vs {t_uniform:.1f} ms uniform"
+
+
+# ---------------------------------------------------------------------------------------------
+# FK open-all: merged radix-8 passes of the small G1 transforms (poly.cu) against one stage per launch and the trapdoor
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("logd", [3, 9, 13, 14])
+def test_open_all_fk_radix8_passes(ctx, logd):
+    """2d = 2^(logd+1) points: logd = 13 ends on a radix-4 pass (14 = 3+3+3+3+2), logd = 14 sends the 2d transform down the
+    large-domain path and the d transform through radix-8 passes; every proof equals the radix-2 build's, a few equal the
+    trapdoor's [(p(tau) - p(w^i)) / (tau - w^i)] G1"""
+    from keaki_b200 import _ffi
+    from keaki_b200.types import Radix2EvaluationDomain
+    d = 1 << logd
+    ctx.srs_generate(L.fr_m(TAU), d, download=False)
+    coeffs = rand_fr_limbs(d)
+    proofs, pinf = ctx.open_all_fk(coeffs)
+    os.environ["KB_NTT_RADIX2"] = "1"
+    try:
+        c2 = _ffi.Context(0)
+    finally:
+        os.environ.pop("KB_NTT_RADIX2", None)
+    try:
+        c2.srs_generate(L.fr_m(TAU), d, download=False)
+        p2, i2 = c2.open_all_fk(coeffs)
+    finally:
+        c2.close()
+    assert np.array_equal(pinf, i2) and np.array_equal(proofs, p2)
+    p = scalars_of(coeffs)
+    dom = Radix2EvaluationDomain(d).elements()
+
+    def ev(z):
+        acc = 0
+        for c in reversed(p):
+            acc = (acc * z + c) % bn.R
+        return acc
+    ptau = ev(TAU)
+    for i in sorted({0, 1, d // 2, d - 1, rng.randrange(d)}):
+        w = int(dom[i])
+        want = bn.g1_mul(bn.G1_GEN, (ptau - ev(w)) * pow(TAU - w, -1, bn.R) % bn.R)
+        assert g1_out(proofs[i], pinf[i]) == want, i
