@@ -124,16 +124,28 @@ static void st_go(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, co
     KB_CUDA(cudaFuncSetAttribute(pairing_st_kernel<BLOCK, MINB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (ctx->device < 64) prepared[ctx->device] = true;
   }
-  unsigned blocks = (unsigned)ctx->sm_count * MINB;
+  // One launch per ROUND (as many pairings as there are resident threads), not one persistent launch for the whole batch:
+  // warps that start a round together stay roughly in step and a round of 37,888 pairings takes 12.9 ms, while the warps
+  // of a persistent launch drift apart and settle at 15-16 ms per round-equivalent (2^18 pairings: 90 ms in rounds against
+  // 112 ms persistent; measured with tools/exp/dec_chunks.py).  Inside a launch the tasks are still dealt dynamically.
+  const unsigned full = (unsigned)ctx->sm_count * MINB;
+  uint64_t round = (uint64_t)full * BLOCK;
+  if (const char* e = getenv("KB_PAIRING_ROUND")) { const uint64_t v = strtoull(e, nullptr, 10); round = v ? v : n; }   // measurement: pairings per launch, 0 = one persistent launch
+  const unsigned rounds = cdiv(n, round);
   const unsigned need = cdiv(n, 32) * 32 / BLOCK + 1;   // never more threads than (padded) pairings
-  if (blocks > need) blocks = need;
-  const size_t threads = (size_t)blocks * BLOCK;
+  const size_t threads = (size_t)(full < need ? full : need) * BLOCK;
   DevBuf<uint4> scratch(ctx, (size_t)st::SCRATCH_SLOTS * 4 * threads);
-  DevBuf<unsigned long long> counter(ctx, 1);
-  KB_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), ctx->stream));
+  DevBuf<unsigned long long> counter(ctx, rounds);
+  KB_CUDA(cudaMemsetAsync(counter.p, 0, rounds * sizeof(unsigned long long), ctx->stream));
   timer_start(ctx, KB_T_PAIRING);
-  KB_LAUNCH(ctx, (pairing_st_kernel<BLOCK, MINB, NS>), blocks, BLOCK, smem, ctx->d_st_consts, d_g1, d_g1_inf, d_g2, d_g2_inf, n, scratch.p, counter.p,
-            mode, d_gt, d_msg_ct, d_off, d_out);
+  for (unsigned r = 0; r < rounds; r++) {
+    const uint64_t lo = (uint64_t)r * round, cnt = n - lo < round ? n - lo : round;
+    unsigned blocks = cdiv(cnt, 32) * 32 / BLOCK + 1;
+    if (blocks > full) blocks = full;
+    KB_LAUNCH(ctx, (pairing_st_kernel<BLOCK, MINB, NS>), blocks, BLOCK, smem, ctx->d_st_consts, d_g1 + 16 * lo, d_g1_inf ? d_g1_inf + lo : nullptr,
+              d_g2 + 32 * lo, d_g2_inf ? d_g2_inf + lo : nullptr, cnt, scratch.p, counter.p + r, mode, d_gt ? d_gt + 96 * lo : nullptr, d_msg_ct,
+              d_off ? d_off + lo : nullptr, d_out);
+  }
   timer_stop(ctx, KB_T_PAIRING);
 }
 
