@@ -113,6 +113,7 @@ struct kb_ctx {
   // compiled single-thread pairing (pairing_st.cu): Frobenius / twist constants; which kernel the batched paths use
   uint32_t* d_st_consts = nullptr;
   int st_shape = 0;
+  int st_segments = 12;              // batches of more than one round: segments per pairing (pairing_st.cu, KB_PAIRING_SEGMENTS)
   int pairing_impl = 1;              // 0 = pairing VM (two lanes + interpreter), 1 = compiled single-thread kernel; KB_PAIRING_IMPL=vm|st
   // warp-cooperative pairing (pairing_warp.cu): dense step descriptors of the two schedules (pairing, GT window bases),
   // their output slots, the Fq2 constants; batches of at most wp_max_n pairings use it (KB_PAIRING_WARP_MAX, 0 = never)

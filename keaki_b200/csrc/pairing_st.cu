@@ -13,6 +13,7 @@
 #include "pairing_st.cuh"
 #include "consts_gen.cuh"
 #include <cstdlib>
+#include <vector>
 
 namespace kb {
 
@@ -112,6 +113,145 @@ __global__ void __launch_bounds__(BLOCK, MINB) pairing_st_kernel(const uint32_t*
   }
 }
 
+// The SEGMENTED form for batches of more than one round.  A round of resident warps (1,184 on a B200) that all run a
+// whole pairing takes 12.9 ms, and a batch is a whole number of such rounds: 2^16 pairings = 2,048 warp tasks = 1.73
+// rounds cost two.  The pairing is a resumable step sequence (pairing_st.cuh), so it is cut into K segments of equal cost
+// and the K x T (segment, task) units are dealt to rounds of 1,184 in segment-major order: segment s of a task runs in a
+// later launch than its segment s - 1, every launch is (nearly) full, and the batch costs ceil(K T / 1184) / K rounds
+// instead of ceil(T / 1184).  Between launches F is parked in the scratch, which is indexed by PAIRING here (not by
+// resident thread), so the G2 accumulator and the saved powers simply stay where they are.
+struct SegBounds { int k; int b[34]; };   // segment s = global steps [b[s], b[s+1]); steps 0..64 Miller loop, 65..257 final exponentiation
+
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) pairing_seg_kernel(const uint32_t* __restrict__ consts, const uint32_t* __restrict__ g1,
+                                                                  const uint8_t* __restrict__ g1_inf, const uint32_t* __restrict__ g2,
+                                                                  const uint8_t* __restrict__ g2_inf, uint64_t n, uint32_t tasks, uint4* __restrict__ scratch,
+                                                                  uint32_t unit_first, uint32_t unit_count, SegBounds sb, int mode,
+                                                                  uint32_t* __restrict__ gt_out, const uint8_t* __restrict__ msg_ct,
+                                                                  const uint64_t* __restrict__ off, uint8_t* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31u, w = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+  if (w >= unit_count) return;                       // whole warps leave
+  const uint32_t u = unit_first + w, seg = u / tasks, task = u % tasks;
+  const uint64_t i = 32ull * task + lane;
+  const bool live = i < n;
+  const uint64_t j = live ? i : n - 1;               // padding lanes recompute the last pairing (in their own scratch column)
+  StDevMem<BLOCK, 12> m;
+  m.gstride = tasks * 32u;
+  m.gl = scratch + i;
+  const int lo = sb.b[seg], hi = sb.b[seg + 1];
+  Fq2 P;
+  P.c0 = fp_load<FqParams>(g1 + 16 * j); P.c1 = fp_load<FqParams>(g1 + 16 * j + 8);
+  if (lo == 0) {
+    Fq2 qx, qy;
+    qx.c0 = fp_load<FqParams>(g2 + 32 * j); qx.c1 = fp_load<FqParams>(g2 + 32 * j + 8);
+    qy.c0 = fp_load<FqParams>(g2 + 32 * j + 16); qy.c1 = fp_load<FqParams>(g2 + 32 * j + 24);
+    m.st(st::G_P, P); m.st(st::G_QX, qx); m.st(st::G_QY, qy);
+  } else {
+#pragma unroll 1
+    for (int s = 0; s < 6; s++) m.st(st::F + s, m.ld(st::G_SAVE_F + s));
+  }
+  if (lo < st::MILLER_STEPS) st::miller_steps(m, consts + 18 * 16, lo, hi < st::MILLER_STEPS ? hi : st::MILLER_STEPS);
+  if (hi > st::MILLER_STEPS) st::final_exp_steps(m, consts, (lo > st::MILLER_STEPS ? lo : st::MILLER_STEPS) - st::MILLER_STEPS, hi - st::MILLER_STEPS);
+  if (hi < st::MILLER_STEPS + st::FE_STEPS) {
+#pragma unroll 1
+    for (int s = 0; s < 6; s++) m.st(st::G_SAVE_F + s, m.ld(st::F + s));
+    return;
+  }
+  const Fq2 qx = m.ld(st::G_QX), qy = m.ld(st::G_QY);
+  const bool trivial = (g1_inf && g1_inf[j]) || (g2_inf && g2_inf[j]) || P.is_zero() || (qx.is_zero() && qy.is_zero());
+  if (mode == 2) {
+    if (live) {
+#pragma unroll 1
+      for (int s = 0; s < 6; s++) {
+        Fq2 x = m.ld(st::F + s);
+        if (trivial) x = s == 0 ? Fq2::one() : Fq2::zero();
+        fp_store<FqParams>(gt_out + 96 * i + 16 * s, x.c0);
+        fp_store<FqParams>(gt_out + 96 * i + 16 * s + 8, x.c1);
+      }
+    }
+    return;
+  }
+  uint32_t wd[96];
+  st::gt_words(m, wd);
+  if (trivial) {   // arkworks skips pairs with an infinity: GT = 1
+#pragma unroll
+    for (int k = 0; k < 96; k++) wd[k] = k == 0 ? 1u : 0u;
+  }
+  if (!live) return;
+  if (mode == 0) {
+    uint4* o = reinterpret_cast<uint4*>(gt_out + 96 * i);
+#pragma unroll
+    for (int k = 0; k < 24; k++) o[k] = make_uint4(wd[4 * k], wd[4 * k + 1], wd[4 * k + 2], wd[4 * k + 3]);
+  } else {
+    const uint64_t lo_b = off[i], hi_b = off[i + 1];
+    b3_gt_xof_xor(wd, msg_ct + lo_b, out + lo_b, hi_b - lo_b);
+  }
+}
+
+// K segments of (nearly) equal cost.  Costs in Fq2-product equivalents: Fq12 square 12, sparse product 13, tangent 11.4, chord
+// 14, cyclotomic square 7.6, Fq12 product 18.
+static SegBounds seg_bounds(int k) {
+  const int total_steps = st::MILLER_STEPS + st::FE_STEPS;
+  std::vector<double> c(total_steps);
+  for (int s = 0; s < 64; s++) c[s] = (s == 0 ? 24.4 : 36.4) + (ate_digit(63 - s) != 0 ? 27.0 : 0.0);
+  c[64] = 56.0;
+  double* f = c.data() + st::MILLER_STEPS;
+  for (int s = 0; s < st::FE_STEPS; s++) {
+    if (s == 0) f[s] = 90.0;
+    else if (s == 64) f[s] = 33.0;
+    else if (s == 128) f[s] = 8.0;
+    else if (s == 192) f[s] = 195.0;
+    else {
+      const int kk = (s - 1) % 64;   // position inside the exponentiation
+      f[s] = kk == 0 ? 62.0 : 7.6 + (st::z_wnaf(62 - kk) != 0 ? 18.0 : 0.0);
+    }
+  }
+  double sum = 0;
+  for (double x : c) sum += x;
+  SegBounds sb{};
+  if (k > 32) k = 32;
+  sb.k = k;
+  sb.b[0] = 0;
+  double acc = 0;
+  int seg = 1;
+  for (int s = 0; s < total_steps && seg < k; s++) {
+    acc += c[s];
+    if (acc >= sum * seg / k) sb.b[seg++] = s + 1;
+  }
+  while (seg <= k) sb.b[seg++] = total_steps;
+  return sb;
+}
+
+template <int BLOCK, int MINB>
+static void seg_go(kb_ctx* ctx, int k, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf, uint64_t n, int mode,
+                   uint32_t* d_gt, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out) {
+  const int smem = BLOCK * 12 * 64;
+  static bool prepared[64] = {};   // function attributes are per device
+  if (ctx->device >= 64 || !prepared[ctx->device]) {
+    KB_CUDA(cudaFuncSetAttribute(pairing_seg_kernel<BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (ctx->device < 64) prepared[ctx->device] = true;
+  }
+  const SegBounds sb = seg_bounds(k);
+  const uint32_t warps_per_round = (uint32_t)ctx->sm_count * MINB * (BLOCK / 32);
+  // the scratch is per pairing: bound it by working through super-chunks of at most 2^17 pairings (0.96 GB), equal in size
+  const uint64_t chunks = cdiv(n, 1ull << 17);
+  const uint64_t per_chunk = cdiv(cdiv(n, chunks), 32) * 32ull;
+  DevBuf<uint4> scratch(ctx, (size_t)(st::SCRATCH_SLOTS + 6) * 4 * per_chunk);
+  timer_start(ctx, KB_T_PAIRING);
+  for (uint64_t lo = 0; lo < n; lo += per_chunk) {
+    const uint64_t cnt = n - lo < per_chunk ? n - lo : per_chunk;
+    const uint32_t tasks = cdiv(cnt, 32);
+    const uint64_t units = (uint64_t)tasks * sb.k;
+    for (uint64_t first = 0; first < units; first += warps_per_round) {
+      const uint32_t count = (uint32_t)(units - first < warps_per_round ? units - first : warps_per_round);
+      KB_LAUNCH(ctx, (pairing_seg_kernel<BLOCK, MINB>), cdiv(count, BLOCK / 32), BLOCK, smem, ctx->d_st_consts, d_g1 + 16 * lo,
+                d_g1_inf ? d_g1_inf + lo : nullptr, d_g2 + 32 * lo, d_g2_inf ? d_g2_inf + lo : nullptr, cnt, tasks, scratch.p, (uint32_t)first, count, sb,
+                mode, d_gt ? d_gt + 96 * lo : nullptr, d_msg_ct, d_off ? d_off + lo : nullptr, d_out);
+    }
+  }
+  timer_stop(ctx, KB_T_PAIRING);
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -156,6 +296,8 @@ void st_init(kb_ctx* ctx) {
   KB_CUDA(cudaMemcpyAsync(ctx->d_st_consts + 19 * 16, consts::TW_Y, 64, cudaMemcpyHostToDevice, ctx->stream));
   ctx->st_shape = 0;
   if (const char* e = getenv("KB_PAIRING_ST_SHAPE")) ctx->st_shape = atoi(e);   // tuning override
+  ctx->st_segments = 12;
+  if (const char* e = getenv("KB_PAIRING_SEGMENTS")) ctx->st_segments = atoi(e);   // 0 / 1: whole pairings per launch
 }
 void st_free(kb_ctx* ctx) { cudaFree(ctx->d_st_consts); ctx->d_st_consts = nullptr; }
 
@@ -163,6 +305,11 @@ void st_pairing_launch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_in
                        int mode, uint32_t* d_gt, const uint8_t* d_msg_ct, const uint64_t* d_off, uint8_t* d_out) {
   // small batches: one WARP per pairing (pairing_warp.cu) - a lone thread here needs 9 ms however few pairings there are
   if (n <= ctx->wp_max_n) { wp_pairing_launch(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out); return; }
+  // more than one round of resident warps: the segmented form packs the rounds (default shape only)
+  if (ctx->st_shape == 0 && ctx->st_segments > 1 && n > (uint64_t)ctx->sm_count * 2 * 128) {
+    seg_go<128, 2>(ctx, ctx->st_segments, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out);
+    return;
+  }
 #define KB_ST_GO(B, MB, NS) st_go<B, MB, NS>(ctx, d_g1, d_g1_inf, d_g2, d_g2_inf, n, mode, d_gt, d_msg_ct, d_off, d_out)
   // Launch shape: 8 warps per SM at 255 registers (two blocks of 128) is the measured optimum on B200 (2^16 pairings:
   // 25.5 ms; 7 warps in one block 27.1, 6 warps 29.5, 12 warps at 168 registers 38.0, 16 warps at 128 registers 37.1 -

@@ -40,6 +40,7 @@ enum : int { F = 0, S = 6, G = 16,
              G_TX = G + 0, G_TY = G + 1, G_TZ = G + 2, G_P = G + 3, G_QX = G + 4, G_QY = G + 5, G_CONJ = G + 12 };
 KB_HD constexpr int G12(int k) { return G + 18 + 6 * k; }   // k-th saved Fq12 of the scratch
 static constexpr int SCRATCH_SLOTS = 18 + 6 * 15;           // Fq2 slots of global scratch per thread
+static constexpr int G_SAVE_F = G + SCRATCH_SLOTS;          // 6 more slots: F between two launches of the segmented form (pairing_st.cu)
 
 // ------------------------------------------------------------------------------------------ Fq2 level
 KB_ST_CALL Fq2 f2mul(Fq2 a, Fq2 b) { return lz::fq2_mul_lazy(a, b); }
@@ -256,94 +257,126 @@ KB_ST_CALL void line_add(M m, Fq2 x2, Fq2 y2) {
   m.st(G_TZ, z3);
 }
 
-// F <- f_{6z+2,Q}(P) l_{pi(Q)} l_{-pi^2(Q)} for P at G_P (x, y packed as one Fq2), Q at G_QX, G_QY (both finite).
-// tw = TW_X || TW_Y (consts_gen.cuh).
+// The pairing as a RESUMABLE sequence of steps: everything that is alive between two steps is in the memory object (F
+// on chip, the G2 accumulator, P, Q and the saved powers in the scratch), so any range of steps can run in one kernel
+// launch and the next range in another (pairing_st.cu packs ranges of equal cost into rounds of resident warps).
+//
+// Miller loop F <- f_{6z+2,Q}(P) l_{pi(Q)} l_{-pi^2(Q)} for P at G_P (x, y packed as one Fq2), Q at G_QX, G_QY (both
+// finite): steps 0..63 are the loop iterations i = 63 - step (step 0 initialises F and T), step 64 the two Frobenius
+// additions.  tw = TW_X || TW_Y (consts_gen.cuh).
+static constexpr int MILLER_STEPS = 65;
 template <class M>
-KB_ST_INL void miller(M& m, const uint32_t* tw) {
-  m.st(F, Fq2::one());
-  for (int i = 1; i < 6; i++) m.st(F + i, Fq2::zero());
-  m.st(G_TX, m.ld(G_QX)); m.st(G_TY, m.ld(G_QY)); m.st(G_TZ, Fq2::one());
-  for (int i = 63; i >= 0; i--) {
-    if (i != 63) f12sqr(m);
-    line_dbl(m);
-    f12mul_line(m);
-    const int d = ate_digit(i);
-    if (d != 0) {
-      const Fq2 qy = m.ld(G_QY);
-      line_add(m, m.ld(G_QX), d > 0 ? qy : -qy);
+KB_ST_INL void miller_steps(M& m, const uint32_t* tw, int lo, int hi) {
+  for (int s = lo; s < hi; s++) {
+    if (s == 0) {
+      m.st(F, Fq2::one());
+      for (int i = 1; i < 6; i++) m.st(F + i, Fq2::zero());
+      m.st(G_TX, m.ld(G_QX)); m.st(G_TY, m.ld(G_QY)); m.st(G_TZ, Fq2::one());
+    }
+    if (s < 64) {
+      const int i = 63 - s;
+      if (i != 63) f12sqr(m);
+      line_dbl(m);
+      f12mul_line(m);
+      const int d = ate_digit(i);
+      if (d != 0) {
+        const Fq2 qy = m.ld(G_QY);
+        line_add(m, m.ld(G_QX), d > 0 ? qy : -qy);
+        f12mul_line(m);
+      }
+    } else {
+      const Fq2 twx = ld_const2(tw), twy = ld_const2(tw + 16);
+      const Fq2 q1x = f2mul(conj(m.ld(G_QX)), twx), q1y = f2mul(conj(m.ld(G_QY)), twy);
+      line_add(m, q1x, q1y);
+      f12mul_line(m);
+      const Fq2 q2x = f2mul(conj(q1x), twx), q2y = -f2mul(conj(q1y), twy);
+      line_add(m, q2x, q2y);
       f12mul_line(m);
     }
   }
-  const Fq2 twx = ld_const2(tw), twy = ld_const2(tw + 16);
-  const Fq2 q1x = f2mul(conj(m.ld(G_QX)), twx), q1y = f2mul(conj(m.ld(G_QY)), twy);
-  line_add(m, q1x, q1y);
-  f12mul_line(m);
-  const Fq2 q2x = f2mul(conj(q1x), twx), q2y = -f2mul(conj(q1y), twy);
-  line_add(m, q2x, q2y);
-  f12mul_line(m);
 }
+template <class M>
+KB_ST_INL void miller(M& m, const uint32_t* tw) { miller_steps(m, tw, 0, MILLER_STEPS); }
 
 // ------------------------------------------------------------------------------------------ final exponentiation
 // width-4 wNAF of z (LSB first; 14 non-zero digits in {+-1, +-3, +-5, +-7}; conjugation is the free inverse)
-KB_ST_INL int z_wnaf(int i) {
+KB_HD int z_wnaf(int i) {
   constexpr signed char d[63] = {1, 0, 0, 0, -1, 0, 0, 0, 0, 5, 0, 0, 0, 0, 0, 0, -7, 0, 0, 0, 7, 0, 0, 0, 0, 5, 0, 0, 0, 0, 1, 0,
                                  0, 0, -3, 0, 0, 0, -5, 0, 0, 0, 5, 0, 0, 0, 0, 3, 0, 0, 0, -3, 0, 0, 0, 0, 5, 0, 0, 0, 0, 0, 1};
   return d[i];
 }
-// F <- F^z (F cyclotomic); table a, a^3, a^5, a^7 at scratch Fq12 slots tb..tb+3, a^2 at tb+4
+// F <- F^z (F cyclotomic) in 63 steps: step 0 builds the table a, a^3, a^5, a^7 at scratch Fq12 slots tb..tb+3 (a^2 at
+// tb+4) and reloads a; step k = 1..62 is the square(-and-multiply) for digit i = 62 - k
 template <class M>
-KB_ST_INL void cyc_exp_z(M& m, int tb) {
-  f12copy(m, G12(tb), F);
-  cycsqr(m);
-  f12copy(m, G12(tb + 4), F);
-  for (int k = 1; k < 4; k++) {
-    f12mul(m, k == 1 ? G12(tb) : G12(tb + 4), 0);   // a^2 a, then (a^(2k-1)) a^2
-    f12copy(m, G12(tb + k), F);
-  }
-  f12copy(m, F, G12(tb));
-  for (int i = 61; i >= 0; i--) {
+KB_ST_INL void cyc_exp_z_step(M& m, int tb, int k) {
+  if (k == 0) {
+    f12copy(m, G12(tb), F);
     cycsqr(m);
-    const int d = z_wnaf(i);
-    if (d != 0) f12mul(m, G12(tb + ((d < 0 ? -d : d) >> 1)), d < 0 ? 1 : 0);
+    f12copy(m, G12(tb + 4), F);
+    for (int j = 1; j < 4; j++) {
+      f12mul(m, j == 1 ? G12(tb) : G12(tb + 4), 0);   // a^2 a, then (a^(2j-1)) a^2
+      f12copy(m, G12(tb + j), F);
+    }
+    f12copy(m, F, G12(tb));
+    return;
   }
+  cycsqr(m);
+  const int d = z_wnaf(62 - k);
+  if (d != 0) f12mul(m, G12(tb + ((d < 0 ? -d : d) >> 1)), d < 0 ? 1 : 0);
 }
 
 // F <- F^((q^6 - 1)(q^2 + 1) lambda): easy part, then the y0..y16 arrangement of the Fuentes-Castaneda hard part that
 // arkworks uses (pairing.cuh final_exponentiation), on one on-chip accumulator with saved values in the scratch.
+// Steps: 0 easy part; 1..63 r^z; 64 glue; 65..127 y3^z; 128 glue; 129..191 y5^z; 192 the closing products.
+static constexpr int FE_STEPS = 193;
 template <class M>
-KB_ST_INL void final_exp(M& m, const uint32_t* gamma) {
+KB_ST_INL void final_exp_steps(M& m, const uint32_t* gamma, int lo, int hi) {
   enum { K_T = 0, K_R = 1, K_Y1 = 2, K_Y3 = 3, K_Y4 = 4, K_Y8 = 5, K_Y9 = 6, K_Y11 = 7, K_Y13 = 8, K_Y14 = 9, K_TAB = 10 };
-  f12copy(m, G12(K_T), F);
-  f12inv(m);
-  f12mul(m, G12(K_T), 1);              // conj(f) / f
-  f12copy(m, G12(K_T), F);
-  f12frob(m, 2, gamma);
-  f12mul(m, G12(K_T), 0);              // r: cyclotomic from here on
-  f12copy(m, G12(K_R), F);
-  cyc_exp_z(m, K_TAB); f12conj(m);     // y0 = r^-z
-  cycsqr(m); f12copy(m, G12(K_Y1), F); // y1
-  cycsqr(m);                           // y2
-  f12mul(m, G12(K_Y1), 0); f12copy(m, G12(K_Y3), F);   // y3 = y2 y1
-  cyc_exp_z(m, K_TAB); f12conj(m); f12copy(m, G12(K_Y4), F);   // y4 = y3^-z
-  cycsqr(m);                           // y5
-  cyc_exp_z(m, K_TAB);                 // y6 = y5^z
-  f12mul(m, G12(K_Y4), 0);             // y7 = y6 y4
-  f12mul(m, G12(K_Y3), 1); f12copy(m, G12(K_Y8), F);   // y8 = y7 conj(y3)
-  f12mul(m, G12(K_Y1), 0); f12copy(m, G12(K_Y9), F);   // y9 = y8 y1
-  f12copy(m, F, G12(K_Y8));
-  f12mul(m, G12(K_Y4), 0);             // y10 = y8 y4
-  f12mul(m, G12(K_R), 0); f12copy(m, G12(K_Y11), F);   // y11 = y10 r
-  f12copy(m, F, G12(K_Y9));
-  f12frob(m, 1, gamma);                // y12
-  f12mul(m, G12(K_Y11), 0); f12copy(m, G12(K_Y13), F); // y13 = y12 y11
-  f12copy(m, F, G12(K_Y8));
-  f12frob(m, 2, gamma);
-  f12mul(m, G12(K_Y13), 0); f12copy(m, G12(K_Y14), F); // y14 = y8^(q^2) y13
-  f12copy(m, F, G12(K_Y9));
-  f12mul(m, G12(K_R), 1);              // conj(r) y9
-  f12frob(m, 3, gamma);                // y15
-  f12mul(m, G12(K_Y14), 0);            // y15 y14
+  for (int s = lo; s < hi; s++) {
+    if (s == 0) {
+      f12copy(m, G12(K_T), F);
+      f12inv(m);
+      f12mul(m, G12(K_T), 1);              // conj(f) / f
+      f12copy(m, G12(K_T), F);
+      f12frob(m, 2, gamma);
+      f12mul(m, G12(K_T), 0);              // r: cyclotomic from here on
+      f12copy(m, G12(K_R), F);
+    } else if (s < 64) {
+      cyc_exp_z_step(m, K_TAB, s - 1);     // ... y0 = r^-z after the conjugation below
+    } else if (s == 64) {
+      f12conj(m);                          // y0
+      cycsqr(m); f12copy(m, G12(K_Y1), F); // y1
+      cycsqr(m);                           // y2
+      f12mul(m, G12(K_Y1), 0); f12copy(m, G12(K_Y3), F);   // y3 = y2 y1
+    } else if (s < 128) {
+      cyc_exp_z_step(m, K_TAB, s - 65);
+    } else if (s == 128) {
+      f12conj(m); f12copy(m, G12(K_Y4), F);   // y4 = y3^-z
+      cycsqr(m);                           // y5
+    } else if (s < 192) {
+      cyc_exp_z_step(m, K_TAB, s - 129);   // y6 = y5^z
+    } else {
+      f12mul(m, G12(K_Y4), 0);             // y7 = y6 y4
+      f12mul(m, G12(K_Y3), 1); f12copy(m, G12(K_Y8), F);   // y8 = y7 conj(y3)
+      f12mul(m, G12(K_Y1), 0); f12copy(m, G12(K_Y9), F);   // y9 = y8 y1
+      f12copy(m, F, G12(K_Y8));
+      f12mul(m, G12(K_Y4), 0);             // y10 = y8 y4
+      f12mul(m, G12(K_R), 0); f12copy(m, G12(K_Y11), F);   // y11 = y10 r
+      f12copy(m, F, G12(K_Y9));
+      f12frob(m, 1, gamma);                // y12
+      f12mul(m, G12(K_Y11), 0); f12copy(m, G12(K_Y13), F); // y13 = y12 y11
+      f12copy(m, F, G12(K_Y8));
+      f12frob(m, 2, gamma);
+      f12mul(m, G12(K_Y13), 0); f12copy(m, G12(K_Y14), F); // y14 = y8^(q^2) y13
+      f12copy(m, F, G12(K_Y9));
+      f12mul(m, G12(K_R), 1);              // conj(r) y9
+      f12frob(m, 3, gamma);                // y15
+      f12mul(m, G12(K_Y14), 0);            // y15 y14
+    }
+  }
 }
+template <class M>
+KB_ST_INL void final_exp(M& m, const uint32_t* gamma) { final_exp_steps(m, gamma, 0, FE_STEPS); }
 
 // canonical (non-Montgomery) little-endian words of F in ark-serialize order (src/kem.rs:31-32,60-61)
 template <class M>

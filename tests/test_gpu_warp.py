@@ -142,3 +142,32 @@ def test_small_encrypt_batches_warp_per_message(ctx, ctx_thread, n):
         k = total if x.dtype == np.uint8 and x.size >= total and x.size != n else x.size
         assert np.array_equal(x[:k], y[:k])
         assert np.array_equal(x[:k], z[:k])
+
+
+def test_segmented_rounds_match_whole_pairings(ctx):
+    """batches of more than one round of resident warps run the pairing as 12 segments packed into rounds (pairing_st.cu);
+    the same batch with whole pairings per launch (KB_PAIRING_SEGMENTS=0) must give the same bytes - incl. infinity operands,
+    a batch size that is not a multiple of 32, and a sample against the C oracle"""
+    from keaki_b200 import _ffi
+    from oracle import coracle as co
+    n = 40000 + 13
+    g1, i1, g2, i2 = _points(ctx, n)
+    i1 = i1.copy(); i2 = i2.copy()
+    i1[[0, 31, 32, 20000, n - 1]] = 1
+    i2[[5, 39999]] = 1
+    got = ctx.pairing_batch(g1, i1, g2, i2)
+    os.environ["KB_PAIRING_SEGMENTS"] = "0"
+    try:
+        c0 = _ffi.Context(0)
+    finally:
+        os.environ.pop("KB_PAIRING_SEGMENTS", None)
+    try:
+        want = c0.pairing_batch(g1, i1, g2, i2)
+    finally:
+        c0.close()
+    assert np.array_equal(got, want)
+    idx = np.array(sorted({0, 1, 5, 31, 32, 33, 12345, 20000, 37887, 37888, 39999, n - 2, n - 1}))
+    ref = co.pairing_batch(np.ascontiguousarray(g1[idx]), np.ascontiguousarray(i1[idx]), np.ascontiguousarray(g2[idx]), np.ascontiguousarray(i2[idx]),
+                           threads=co.max_threads())
+    assert np.array_equal(got[idx], ref)
+    assert bytes(got[0]) == KAT_GT_ONE_BYTES and bytes(got[5]) == KAT_GT_ONE_BYTES
