@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(128) encrypt_kernel(const uint32_t* __restrict
 }
 
 // ct = r tau_2 - (r alpha) G2
-__global__ void __launch_bounds__(128, 3) encrypt_ct_kernel(const uint32_t* __restrict__ tau2_tab, const uint32_t* __restrict__ g2_tab,
+__global__ void __launch_bounds__(128, 4) encrypt_ct_kernel(const uint32_t* __restrict__ tau2_tab, const uint32_t* __restrict__ g2_tab,
                                                             const uint32_t* __restrict__ points, const uint32_t* __restrict__ rs, uint64_t n,
                                                             uint32_t* __restrict__ ct, uint8_t* __restrict__ ct_inf) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
