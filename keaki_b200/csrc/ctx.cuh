@@ -113,6 +113,7 @@ struct kb_ctx {
   // compiled single-thread pairing (pairing_st.cu): Frobenius / twist constants; which kernel the batched paths use
   uint32_t* d_st_consts = nullptr;
   int st_shape = 0;
+  bool enc_gt_st = true;             // GT side of encrypt on the shared-memory Fq12 machinery of pairing_st (KB_ENCRYPT_GT=tower: we.cu's generic code)
   int st_segments = 12;              // batches of more than one round: segments per pairing (pairing_st.cu, KB_PAIRING_SEGMENTS)
   int pairing_impl = 1;              // 0 = pairing VM (two lanes + interpreter), 1 = compiled single-thread kernel; KB_PAIRING_IMPL=vm|st
   // warp-cooperative pairing (pairing_warp.cu): dense step descriptors of the two schedules (pairing, GT window bases),
@@ -279,6 +280,8 @@ void wp_encrypt_small_launch(kb_ctx* ctx, const uint32_t* com_tab_a, const uint3
                              const uint32_t* tau2_tab16, const uint32_t* g2_tab16, const uint32_t* d_points, const uint32_t* d_values,
                              const uint32_t* d_r, const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n, uint32_t* d_ct, uint8_t* d_ct_inf,
                              uint8_t* d_msg_ct);
+void st_encrypt_gt_launch(kb_ctx* ctx, const uint32_t* com_tab_a, const uint32_t* com_tab_a1, const uint32_t* gt_tab16, const uint32_t* d_values,
+                          const uint32_t* d_r, const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n, int com_wide, uint8_t* d_msg_ct);
 void pairing_batch(kb_ctx* ctx, const uint32_t* d_g1, const uint8_t* d_g1_inf, const uint32_t* d_g2, const uint8_t* d_g2_inf,
                    uint64_t n, uint8_t* d_gt_bytes);
 void decrypt_batch(kb_ctx* ctx, const uint32_t* d_proofs, const uint8_t* d_pinf, const uint32_t* d_ct, const uint8_t* d_cinf,

@@ -13,6 +13,7 @@
 #include "pairing_st.cuh"
 #include "consts_gen.cuh"
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 namespace kb {
@@ -111,6 +112,81 @@ __global__ void __launch_bounds__(BLOCK, MINB) pairing_st_kernel(const uint32_t*
       b3_gt_xof_xor(w, msg_ct + lo, out + lo, hi - lo);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// GT side of `encrypt` on the same machinery: secret = prod_w table[w][digit_w] as a chain of Fq12 products with the
+// accumulator in shared memory and lazily reduced Fq2 products (18 x 320 IMAD.WIDE per Fq12 product, no stack traffic),
+// instead of the generic tower code of we.cu (54 full Montgomery products = 6,912 IMAD.WIDE, Fq12 values on the thread
+// stack).  Same table entries in the same order: the same GT element, bit for bit.
+// ------------------------------------------------------------------------------------------
+__device__ const uint32_t GT_ONE_LIMBS[96] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+
+template <int BLOCK>
+struct EncMem {          // addresses 0..11: F and S on chip; 16..21: the six Fq2 of the table entry `ent` (read only)
+  const uint32_t* ent;
+  __device__ __forceinline__ Fq2 ld(int a) const {
+    if (a < 12) {
+      const uint4* p = st_smem + (size_t)(4 * a) * BLOCK + threadIdx.x;
+      return StDevMem<BLOCK, 12>::unpack(p[0], p[BLOCK], p[2 * BLOCK], p[3 * BLOCK]);
+    }
+    const uint4* p = reinterpret_cast<const uint4*>(ent + 16 * (a - 16));
+    return StDevMem<BLOCK, 12>::unpack(p[0], p[1], p[2], p[3]);
+  }
+  __device__ __forceinline__ void st(int a, const Fq2& x) const {
+    uint4* p = st_smem + (size_t)(4 * a) * BLOCK + threadIdx.x;
+    p[0] = make_uint4(x.c0.v[0], x.c0.v[1], x.c0.v[2], x.c0.v[3]); p[BLOCK] = make_uint4(x.c0.v[4], x.c0.v[5], x.c0.v[6], x.c0.v[7]);
+    p[2 * BLOCK] = make_uint4(x.c1.v[0], x.c1.v[1], x.c1.v[2], x.c1.v[3]); p[3 * BLOCK] = make_uint4(x.c1.v[4], x.c1.v[5], x.c1.v[6], x.c1.v[7]);
+  }
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 2) encrypt_gt_st_kernel(const uint32_t* __restrict__ com_tab_a, const uint32_t* __restrict__ com_tab_a1,
+                                                                 const uint32_t* __restrict__ gt_tab, const uint32_t* __restrict__ values,
+                                                                 const uint32_t* __restrict__ rs, const uint8_t* __restrict__ msgs,
+                                                                 const uint64_t* __restrict__ off, uint64_t n, int com_wide, uint8_t* __restrict__ msg_ct) {
+  const uint64_t i0 = blockIdx.x * (uint64_t)BLOCK + threadIdx.x;
+  const bool live = i0 < n;
+  const uint64_t i = live ? i0 : n - 1;              // padding lanes recompute the last message (warps stay whole)
+  const Fr r = fp_load<FrParams>(rs + 8 * i), v = fp_load<FrParams>(values + 8 * i);
+  const Fr kr = fp_from_mont<FrParams>(r);
+  const bool v_one = v == Fr::one(), v_bit = v_one || v.is_zero();
+  const uint32_t* com_tab = v_one ? com_tab_a1 : com_tab_a;
+  const Fr ks = v_bit ? Fr::zero() : fp_from_mont<FrParams>(-(v * r));
+  EncMem<BLOCK> m;
+  const int nwin = com_wide ? WE_WIN16 : WE_WIN;
+#pragma unroll 1
+  for (int w = 0; w < nwin; w++) {
+    const uint32_t d = com_wide ? half_of(kr.v, w) : byte_of(kr.v, w);
+    m.ent = d ? com_tab + 96 * ((size_t)w * (com_wide ? WE_ENT16 : WE_ENT) + d - 1) : GT_ONE_LIMBS;
+    if (w == 0) { for (int k = 0; k < 6; k++) m.st(st::F + k, m.ld(16 + k)); }
+    else st::f12mul(m, 16, 0);
+  }
+  if (__any_sync(0xffffffffu, !v_bit)) {             // general values: times gT^(-v r); bit-valued lanes multiply by one
+#pragma unroll 1
+    for (int w = 0; w < WE_WIN16; w++) {
+      const uint32_t d = half_of(ks.v, w);
+      m.ent = d ? gt_tab + 96 * ((size_t)w * WE_ENT16 + d - 1) : GT_ONE_LIMBS;
+      st::f12mul(m, 16, 0);
+    }
+  }
+  uint32_t wd[96];
+  st::gt_words(m, wd);
+  if (!live) return;
+  const uint64_t lo = off[i], hi = off[i + 1];
+  b3_gt_xof_xor(wd, msgs + lo, msg_ct + lo, hi - lo);
+}
+
+void st_encrypt_gt_launch(kb_ctx* ctx, const uint32_t* com_tab_a, const uint32_t* com_tab_a1, const uint32_t* gt_tab16, const uint32_t* d_values,
+                          const uint32_t* d_r, const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n, int com_wide, uint8_t* d_msg_ct) {
+  constexpr int BLOCK = 128;
+  const int smem = BLOCK * 12 * 64;
+  static bool prepared[64] = {};
+  if (ctx->device >= 64 || !prepared[ctx->device]) {
+    KB_CUDA(cudaFuncSetAttribute(encrypt_gt_st_kernel<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (ctx->device < 64) prepared[ctx->device] = true;
+  }
+  KB_LAUNCH(ctx, (encrypt_gt_st_kernel<BLOCK>), cdiv(n, BLOCK), BLOCK, smem, com_tab_a, com_tab_a1, gt_tab16, d_values, d_r, d_msgs, d_off, n, com_wide, d_msg_ct);
 }
 
 // The SEGMENTED form for batches of more than one round.  A round of resident warps (1,184 on a B200) that all run a
@@ -296,6 +372,8 @@ void st_init(kb_ctx* ctx) {
   KB_CUDA(cudaMemcpyAsync(ctx->d_st_consts + 19 * 16, consts::TW_Y, 64, cudaMemcpyHostToDevice, ctx->stream));
   ctx->st_shape = 0;
   if (const char* e = getenv("KB_PAIRING_ST_SHAPE")) ctx->st_shape = atoi(e);   // tuning override
+  ctx->enc_gt_st = true;
+  if (const char* e = getenv("KB_ENCRYPT_GT")) ctx->enc_gt_st = std::string(e) != "tower";   // tower = the generic Fq12 code of we.cu
   ctx->st_segments = 12;
   if (const char* e = getenv("KB_PAIRING_SEGMENTS")) ctx->st_segments = atoi(e);   // 0 / 1: whole pairings per launch
 }

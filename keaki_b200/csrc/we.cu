@@ -298,8 +298,12 @@ void encrypt_batch(kb_ctx* ctx, const uint32_t* h_com_xy, uint8_t com_inf, const
     return;
   }
   timer_start(ctx, KB_T_ENCRYPT);
-  KB_LAUNCH(ctx, encrypt_kernel, cdiv(n, 128), 128, 0, wide ? ctx->d_com_tab16 : ctx->d_com_tab, wide ? ctx->d_com1_tab16 : ctx->d_com1_tab,
-            ctx->d_gt_tab16, d_values, d_r, d_msgs, d_off, n, wide ? 1 : 0, d_msg_ct);
+  if (ctx->enc_gt_st)
+    st_encrypt_gt_launch(ctx, wide ? ctx->d_com_tab16 : ctx->d_com_tab, wide ? ctx->d_com1_tab16 : ctx->d_com1_tab, ctx->d_gt_tab16, d_values, d_r, d_msgs,
+                         d_off, n, wide ? 1 : 0, d_msg_ct);
+  else
+    KB_LAUNCH(ctx, encrypt_kernel, cdiv(n, 128), 128, 0, wide ? ctx->d_com_tab16 : ctx->d_com_tab, wide ? ctx->d_com1_tab16 : ctx->d_com1_tab,
+              ctx->d_gt_tab16, d_values, d_r, d_msgs, d_off, n, wide ? 1 : 0, d_msg_ct);
   KB_LAUNCH(ctx, encrypt_ct_kernel, cdiv(n, 128), 128, 0, ctx->d_tau2_tab16, ctx->d_g2_tab16, d_points, d_r, n, d_ct, d_ct_inf);
   timer_stop(ctx, KB_T_ENCRYPT);
 }
