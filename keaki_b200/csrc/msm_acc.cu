@@ -11,7 +11,7 @@ namespace kb {
 // entries one thread sums at most (see "Over-full buckets" below): above the largest bucket uniform scalars produce
 // (26 +- 5 at 2^20 - 109 in the 12,388 buckets the 15-bit top window of a scalar below r reaches - 32 +- 6 at 2^16) and short enough that a lone thread's chain (5 us per dependent addition) stays
 // well below the kernel's own time
-static constexpr uint32_t MSM_SEG = 128;
+static constexpr uint32_t MSM_SEG = 256;   // above the fullest bucket of uniform scalars: the top window of c = 20 has 14 bits below r, 6,194 buckets of 169 entries on average at 2^20 points
 
 // ------------------------------------------------------------------------------------------
 // bucket accumulation: one thread per bucket, XYZZ mixed additions, next base prefetched
