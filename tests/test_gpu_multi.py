@@ -99,3 +99,23 @@ def test_multi_encrypt_decrypt_identical_to_single(ctxs):
     out_m = multi.decrypt_batch(proofs, pinf, ct_m, ci_m, mc_m, off)
     out_s = single.decrypt_batch(proofs, pinf, ct_s, ci_s, mc_s, off)
     assert np.array_equal(out_m, out_s)
+
+
+def test_multi_large_decrypt_segmented_per_device(ctxs):
+    """a batch large enough that EVERY device runs the segmented pairing launches (more than one round of resident warps per
+    device): sharded result identical to the single-device context, which runs the same batch as 2+ rounds itself"""
+    multi, single = ctxs
+    n = multi.device_count() * 38000 + 77
+    for c in (multi, single):
+        c.srs_generate(L.fr_m(TAU), 256, download=False)
+    com = bn.g1_mul(bn.G1_GEN, rng.randrange(1, bn.R))
+    pts, rs = rand_fr_limbs(n), rand_fr_limbs(n)
+    vals = np.zeros((n, 8), np.uint32)
+    off = np.arange(n + 1, dtype=np.uint64) * 32
+    msgs = nprng.integers(0, 256, size=32 * n, dtype=np.uint8)
+    ct, ci, mc = single.encrypt_batch(L.g1_m(com), 0, pts, vals, rs, msgs, off)
+    proofs, pinf = single.g1_mul_gen_batch(rand_fr_limbs(n))
+    pinf[[0, 37999, 38000, n - 1]] = 1
+    out_m = multi.decrypt_batch(proofs, pinf, ct, ci, mc, off)
+    out_s = single.decrypt_batch(proofs, pinf, ct, ci, mc, off)
+    assert np.array_equal(out_m, out_s)
