@@ -51,6 +51,18 @@ vm_ctx = _ffi.Context(0)
 out_vm = vm_ctx.decrypt_batch(proofs, pinf, ct, cti, mc, off)
 assert np.array_equal(out, out_vm)
 vm_ctx.close()
+# above the small-batch thresholds: the GT encrypt kernel on the pairing's shared-memory machinery, the thread-per-message G2
+# kernel, and the SEGMENTED pairing launches (more than one round of resident warps)
+nb = 2100
+ptsb, valsb = rnd(nb), rnd(nb); valsb[:700] = fr_to_limbs(0); valsb[700:1400] = fr_to_limbs(1)
+offb = np.arange(nb + 1, dtype=np.uint64) * 32
+ctb, ctib, mcb = ctx.encrypt_batch(com, ci, ptsb, valsb, rnd(nb), rng.integers(0, 256, size=nb * 32, dtype=np.uint8), offb)
+nbig = 148 * 256 + 200
+g1b, i1b = ctx.g1_mul_gen_batch(rnd(64))
+g1big = np.ascontiguousarray(np.tile(g1b, (nbig // 64 + 1, 1))[:nbig]); i1big = np.zeros(nbig, np.uint8); i1big[[0, 37888, nbig - 1]] = 1
+g2big = np.ascontiguousarray(np.tile(ctb[:64], (nbig // 64 + 1, 1))[:nbig]); i2big = np.zeros(nbig, np.uint8)
+gt_big = ctx.pairing_batch(g1big, i1big, g2big, i2big)
+assert np.array_equal(gt_big[64:128], gt_big[128:192]) and np.array_equal(gt_big[1], gt_big[37888 + 64 - 37888 % 64 + 1])
 ok = ctx.verify_batch(np.tile(com, (n, 1)), np.zeros(n, np.uint8), pts, vals, proofs, pinf)
 b = ctx.g2_serialize(ct, cti, True)
 back = ctx.g2_deserialize(b, True, True)
