@@ -52,7 +52,7 @@ int main() {
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
       }
       const int streams = mode == 0 ? 1 : mode == 3 ? 4 : 2;
-      printf("warps/SM %d mode %d: %.3f ms, %.1f ns per product per warp, %.2f products/us/SM\n", warps, mode, best,
+      printf("warps/SM %d mode %d: %.3f ms, %.1f ns per product per warp, %.2f warp-products/us/SM (x 32 per thread)\n", warps, mode, best,
              best * 1e6 / iters / streams, (double)iters * streams * warps / (best * 1e3));
     }
   }
